@@ -1,0 +1,233 @@
+// api.cu — the extern "C" boundary of libbuffer_b200.so (declared in include/buffer_b200.h).
+#include "../../include/buffer_b200.h"
+#include "bfr_kernels.h"
+
+using namespace bfr;
+
+namespace {
+
+inline int cu(cudaError_t e) { return e == cudaSuccess ? BFR_OK : (int)e; }
+inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+inline size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline cudaStream_t st(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__global__ void uniform_offsets_kernel(int32_t* off_m, int32_t* off_n, int P, int M, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= P) { off_m[i] = i * M; off_n[i] = i * N; }
+}
+
+// carve-up of the bfr_register_batched workspace
+struct RegWs {
+    void* k1; float* corr; unsigned long long* best; float* T0;
+};
+inline size_t reg_ws_bytes(int P, int max_M, int max_N, int total_M)
+{
+    return up256(k1_workspace_bytes(P, max_M, max_N)) + up256((size_t)(total_M > 0 ? total_M : 1) * 32) + up256((size_t)P * 8) + up256((size_t)P * 64) + 256;
+}
+inline RegWs reg_ws_carve(void* ws, int P, int max_M, int max_N, int total_M)
+{
+    unsigned char* w = reinterpret_cast<unsigned char*>(up256((size_t)(uintptr_t)ws));
+    RegWs r;
+    r.k1 = w; w += up256(k1_workspace_bytes(P, max_M, max_N));
+    r.corr = reinterpret_cast<float*>(w); w += up256((size_t)(total_M > 0 ? total_M : 1) * 32);
+    r.best = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)P * 8);
+    r.T0 = reinterpret_cast<float*>(w);
+    return r;
+}
+
+}  // namespace
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+int bfr_version(void) { return 100; }
+
+const char* bfr_error_string(int code)
+{
+    switch (code) {
+        case BFR_OK: return "ok";
+        case BFR_E_NULL: return "required pointer is NULL";
+        case BFR_E_SIZE: return "negative or inconsistent size";
+        case BFR_E_DIM: return "unsupported descriptor length (this build supports D == 32)";
+        case BFR_E_WORKSPACE: return "workspace too small";
+        case BFR_E_ALIGN: return "pointer not 16-byte aligned";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+size_t bfr_mutual_nn_workspace_bytes(int P, int max_M, int max_N) { return k1_workspace_bytes(P < 0 ? 0 : P, max_M, max_N); }
+
+int bfr_mutual_matching_batched(const float* src_des, const float* tgt_des, const int32_t* src_off, const int32_t* tgt_off,
+                                int P, int max_M, int max_N, int D, int col_splits,
+                                int64_t* nn_s, int64_t* nn_t, float* dist_s, float* dist_t,
+                                const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr_xyz,
+                                void* ws, size_t ws_bytes, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!src_des || !tgt_des || !src_off || !tgt_off || !ws) return BFR_E_NULL;
+    if (P < 0 || max_M < 0 || max_N < 0) return BFR_E_SIZE;
+    if (D != 32) return BFR_E_DIM;
+    if (!aligned16(src_des) || !aligned16(tgt_des)) return BFR_E_ALIGN;
+    if (ws_bytes < k1_workspace_bytes(P, max_M, max_N)) return BFR_E_WORKSPACE;
+    if (corr_xyz && (!src_xyz || !tgt_xyz)) return BFR_E_NULL;
+    if ((s_mids == nullptr) != (t_mids == nullptr)) return BFR_E_NULL;
+    return cu(k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, D, col_splits, ws, nn_s, nn_t, dist_s, dist_t,
+                        src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, corr_xyz, st(stream)));
+}
+
+int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr_xyz, void* stream)
+{
+    if (K == 0) return BFR_OK;
+    if (!src_xyz || !tgt_xyz || !s_ids || !t_ids || !corr_xyz) return BFR_E_NULL;
+    if (K < 0) return BFR_E_SIZE;
+    return cu(gather_corr_launch(src_xyz, tgt_xyz, s_ids, t_ids, K, corr_xyz, st(stream)));
+}
+
+int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
+                       uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
+                       float dist_th, float similar_th, int splits, uint64_t* best_packed, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!corr_xyz || !corr_off || !corr_cnt || !best_packed) return BFR_E_NULL;
+    if (P < 0 || h_end < h_begin) return BFR_E_SIZE;
+    if (!aligned16(corr_xyz)) return BFR_E_ALIGN;
+    return cu(ransac_launch(corr_xyz, corr_off, corr_cnt, P, seed, pair_id_base, h_begin, h_end, dist_th, similar_th, splits,
+                            reinterpret_cast<unsigned long long*>(best_packed), st(stream)));
+}
+
+int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
+                                uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th, const uint64_t* best_packed,
+                                float* T, int32_t* inliers, int64_t* best_h, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!corr_xyz || !corr_off || !corr_cnt || !best_packed || !T) return BFR_E_NULL;
+    if (P < 0) return BFR_E_SIZE;
+    return cu(ransac_finalize_launch(corr_xyz, corr_off, corr_cnt, P, seed, pair_id_base, dist_th, similar_th,
+                                     reinterpret_cast<const unsigned long long*>(best_packed), T, inliers, best_h, st(stream)));
+}
+
+int bfr_lrf_hypotheses(const float* cs, const float* ss_R, const float* tt_R, const float* ss_kpts, const float* tt_kpts, int A,
+                       float* R_out, float* t_out, void* stream)
+{
+    if (A == 0) return BFR_OK;
+    if (!cs || !ss_R || !tt_R || !ss_kpts || !tt_kpts || !R_out || !t_out) return BFR_E_NULL;
+    if (A < 0) return BFR_E_SIZE;
+    return cu(lrf_hypotheses_launch(cs, ss_R, tt_R, ss_kpts, tt_kpts, A, R_out, t_out, st(stream)));
+}
+
+size_t bfr_score_workspace_bytes(int C) { return score_workspace_bytes(C); }
+
+int bfr_score_hypotheses(const float* R, const float* t, int H, const float* src, const float* tgt, int C, const float* thr, float thr_scalar,
+                         int32_t* counts, uint64_t* best_packed, int64_t* best_idx, uint8_t* mask, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!best_packed || !ws) return BFR_E_NULL;
+    if (H < 0 || C < 0) return BFR_E_SIZE;
+    if (H > 0 && (!R || !t)) return BFR_E_NULL;
+    if (C > 0 && (!src || !tgt)) return BFR_E_NULL;
+    if (ws_bytes < score_workspace_bytes(C)) return BFR_E_WORKSPACE;
+    return cu(score_hypotheses_launch(R, t, H, src, tgt, C, thr, thr_scalar, counts, reinterpret_cast<unsigned long long*>(best_packed),
+                                      best_idx, mask, ws, st(stream)));
+}
+
+int bfr_rigid_transform_3d(const float* A, const float* B, const float* w, int bs, int n, float weight_threshold, float* T, void* stream)
+{
+    if (bs == 0) return BFR_OK;
+    if (!A || !B || !T) return BFR_E_NULL;
+    if (bs < 0 || n < 0) return BFR_E_SIZE;
+    return cu(rigid_transform_launch(A, B, w, bs, n, weight_threshold, T, st(stream)));
+}
+
+int bfr_post_refinement_batched(const float* T0, const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
+                                float thr, int max_iter, float* T_out, int32_t* iters, int32_t* inliers, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!T0 || !corr_xyz || !corr_off || !corr_cnt || !T_out) return BFR_E_NULL;
+    if (P < 0 || max_iter < 0) return BFR_E_SIZE;
+    return cu(post_refinement_launch(T0, corr_xyz, corr_off, corr_cnt, P, thr, max_iter, T_out, iters, inliers, st(stream)));
+}
+
+size_t bfr_register_workspace_bytes(int P, int max_M, int max_N, int total_M, int total_N)
+{
+    (void)total_N;
+    return reg_ws_bytes(P < 0 ? 0 : P, max_M, max_N, total_M);
+}
+
+int bfr_register_batched(const float* src_des, const float* src_xyz, const int32_t* src_off,
+                         const float* tgt_des, const float* tgt_xyz, const int32_t* tgt_off,
+                         int P, int max_M, int max_N, int total_M, int total_N, int D,
+                         int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th,
+                         float refine_thr, int refine_iters, int ransac_splits,
+                         float* T_out, int32_t* n_mutual, int32_t* n_inliers, void* ws, size_t ws_bytes, void* stream)
+{
+    (void)total_N;
+    if (P == 0) return BFR_OK;
+    if (!src_des || !src_xyz || !src_off || !tgt_des || !tgt_xyz || !tgt_off || !T_out || !n_mutual || !ws) return BFR_E_NULL;
+    if (P < 0 || max_M < 0 || max_N < 0 || total_M < 0 || hypotheses < 0 || refine_iters < 0) return BFR_E_SIZE;
+    if (D != 32) return BFR_E_DIM;
+    if (!aligned16(src_des) || !aligned16(tgt_des)) return BFR_E_ALIGN;
+    if (ws_bytes < reg_ws_bytes(P, max_M, max_N, total_M)) return BFR_E_WORKSPACE;
+    cudaStream_t s = st(stream);
+    RegWs w = reg_ws_carve(ws, P, max_M, max_N, total_M);
+    cudaError_t e = cudaMemsetAsync(w.best, 0, (size_t)P * 8, s);
+    if (e != cudaSuccess) return (int)e;
+    e = k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, D, 1, w.k1, nullptr, nullptr, nullptr, nullptr,
+                  src_xyz, tgt_xyz, nullptr, nullptr, n_mutual, w.corr, s);
+    if (e != cudaSuccess) return (int)e;
+    e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, ransac_splits, w.best, s);
+    if (e != cudaSuccess) return (int)e;
+    float* T_ransac = refine_iters > 0 ? w.T0 : T_out;
+    e = ransac_finalize_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, dist_th, similar_th, w.best, T_ransac, n_inliers, nullptr, s);
+    if (e != cudaSuccess) return (int)e;
+    if (refine_iters > 0) e = post_refinement_launch(w.T0, w.corr, src_off, n_mutual, P, refine_thr, refine_iters, T_out, nullptr, nullptr, s);
+    return cu(e);
+}
+
+size_t bfr_register_host_workspace_bytes(int P, int M, int N, int D)
+{
+    if (P < 0 || M < 0 || N < 0 || D < 0) return 0;
+    const size_t tm = (size_t)P * M, tn = (size_t)P * N;
+    return reg_ws_bytes(P, M, N, (int)tm) + up256(tm * D * 4) + up256(tn * D * 4) + up256(tm * 12) + up256(tn * 12) +
+           2 * up256((size_t)(P + 1) * 4) + up256((size_t)P * 64) + 2 * up256((size_t)P * 4) + 512;
+}
+
+int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_host, const float* tgt_des_host, const float* tgt_xyz_host,
+                              int P, int M, int N, int D, int hypotheses, uint64_t seed, uint32_t pair_id_base,
+                              float dist_th, float similar_th, float refine_thr, int refine_iters, int ransac_splits,
+                              float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host, void* ws, size_t ws_bytes, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!src_des_host || !src_xyz_host || !tgt_des_host || !tgt_xyz_host || !T_out_host || !ws) return BFR_E_NULL;
+    if (P < 0 || M < 0 || N < 0) return BFR_E_SIZE;
+    if (D != 32) return BFR_E_DIM;
+    if (ws_bytes < bfr_register_host_workspace_bytes(P, M, N, D)) return BFR_E_WORKSPACE;
+    cudaStream_t s = st(stream);
+    const size_t tm = (size_t)P * M, tn = (size_t)P * N;
+    unsigned char* w = reinterpret_cast<unsigned char*>(up256((size_t)(uintptr_t)ws));
+    float* d_sdes = reinterpret_cast<float*>(w); w += up256(tm * D * 4);
+    float* d_tdes = reinterpret_cast<float*>(w); w += up256(tn * D * 4);
+    float* d_sxyz = reinterpret_cast<float*>(w); w += up256(tm * 12);
+    float* d_txyz = reinterpret_cast<float*>(w); w += up256(tn * 12);
+    int32_t* d_offm = reinterpret_cast<int32_t*>(w); w += up256((size_t)(P + 1) * 4);
+    int32_t* d_offn = reinterpret_cast<int32_t*>(w); w += up256((size_t)(P + 1) * 4);
+    float* d_T = reinterpret_cast<float*>(w); w += up256((size_t)P * 64);
+    int32_t* d_nm = reinterpret_cast<int32_t*>(w); w += up256((size_t)P * 4);
+    int32_t* d_ni = reinterpret_cast<int32_t*>(w); w += up256((size_t)P * 4);
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(d_sdes, src_des_host, tm * D * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpyAsync(d_tdes, tgt_des_host, tn * D * 4, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpyAsync(d_sxyz, src_xyz_host, tm * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpyAsync(d_txyz, tgt_xyz_host, tn * 12, cudaMemcpyHostToDevice, s)) != cudaSuccess) return (int)e;
+    uniform_offsets_kernel<<<(P + 256) / 256, 256, 0, s>>>(d_offm, d_offn, P, M, N);
+    const size_t inner = reg_ws_bytes(P, M, N, (int)tm);
+    int rc = bfr_register_batched(d_sdes, d_sxyz, d_offm, d_tdes, d_txyz, d_offn, P, M, N, (int)tm, (int)tn, D, hypotheses, seed, pair_id_base,
+                                  dist_th, similar_th, refine_thr, refine_iters, ransac_splits, d_T, d_nm, d_ni, w, inner, stream);
+    if (rc != BFR_OK) return rc;
+    if ((e = cudaMemcpyAsync(T_out_host, d_T, (size_t)P * 64, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
+    if (n_mutual_host && (e = cudaMemcpyAsync(n_mutual_host, d_nm, (size_t)P * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
+    if (n_inliers_host && (e = cudaMemcpyAsync(n_inliers_host, d_ni, (size_t)P * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
+    return BFR_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,34 @@
+// bfr_kernels.h — internal launcher declarations (host side) shared by the .cu files and the C ABI (api.cu).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace bfr {
+
+// K1 (mutual_nn.cu)
+int k1_pad_rows(int max_rows);
+size_t k1_workspace_bytes(int P, int max_M, int max_N);
+cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N, int D,
+                      int col_splits, void* ws, int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t,
+                      const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr,
+                      cudaStream_t stream);
+cudaError_t gather_corr_launch(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr, cudaStream_t stream);
+
+// K2 + K3 (ransac.cu)
+cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
+                          uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, int splits, unsigned long long* best_packed, cudaStream_t stream);
+cudaError_t ransac_finalize_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
+                                   float dist_th, float similar_th, const unsigned long long* best_packed, float* T, int32_t* inliers, int64_t* best_h, cudaStream_t stream);
+cudaError_t lrf_hypotheses_launch(const float* cs, const float* ss_R, const float* tt_R, const float* ss_kpts, const float* tt_kpts, int A,
+                                  float* R_out, float* t_out, cudaStream_t stream);
+size_t score_workspace_bytes(int C);
+cudaError_t score_hypotheses_launch(const float* R, const float* t, int H, const float* src, const float* tgt, int C, const float* thr, float thr_scalar,
+                                    int32_t* counts, unsigned long long* best_packed, int64_t* best_idx, uint8_t* mask, void* ws, cudaStream_t stream);
+
+// K4 (refine.cu)
+cudaError_t rigid_transform_launch(const float* A, const float* B, const float* w, int bs, int n, float weight_threshold, float* T, cudaStream_t stream);
+cudaError_t post_refinement_launch(const float* T0, const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, float thr, int max_iter,
+                                   float* Tout, int32_t* iters_out, int32_t* inliers_out, cudaStream_t stream);
+
+}  // namespace bfr

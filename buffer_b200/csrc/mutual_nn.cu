@@ -1,0 +1,334 @@
+// mutual_nn.cu — K1: fused descriptor L2 distance + mutual-nearest-neighbour argmin for sm_100a.
+//
+// Replaces buffer.mutual_matching (reference models/BUFFER.py:335-359): two knn_cuda.KNN(k=1) brute-force passes that
+// materialise the N x M distance matrix in HBM, two device->host syncs and a numpy mutual check.  Here one pass
+// computes every a_i.b_j once, reduces row maxima (src -> tgt NN) and column maxima (tgt -> src NN) on the fly and
+// never stores the matrix.  Arithmetic (bit-exact with oracle/bfr_oracle.c orc_mutual_nn):
+//     acc_ij = -|b_j|^2/2, then acc_ij = fma(a_ik, b_jk, acc_ij) for k = 0..31;   nn_s[i] = argmax_j acc_ij,
+//     nn_t[j] = argmax_i (acc_ij - |a_i|^2/2);   ties -> lowest index (packed 64-bit max of (key << 32 | ~index)).
+//
+// Design ("row-stationary"): a thread keeps 4 source rows x 32 dims in registers as two packed row pairs, so the
+// inner product is FFMA2 (fma.rn.f32x2: two rows per instruction) against a target value that every lane of the warp
+// reads from the same shared-memory address (LDS.128 broadcast: 4 dims per load, no bank conflicts, no swizzle).
+// Target rows stream through a 4-stage shared-memory ring filled by 1-D TMA bulk copies (cp.async.bulk + mbarrier).
+// Row maxima are thread-local (value-only FMNMX3 per 8-column chunk, index recovered only when the chunk improves the
+// running maximum); column maxima are one CREDUX (redux.sync.max.f32) per column per warp, the winning lane publishes
+// with a 64-bit atomicMax.  Issue-slot accounting and the measured roofline are in DESIGN.md §K1.
+#include "bfr_common.cuh"
+#include "bfr_kernels.h"
+#include <cfloat>
+#include <cmath>
+
+namespace bfr {
+
+constexpr int K1_D = 32;                      // descriptor length (BUFFER: Cylindrical_Net dim=32, models/patchnet.py:69-85)
+constexpr int K1_WARPS = 4;
+constexpr int K1_THREADS = K1_WARPS * 32;
+constexpr int K1_RPT = 4;                     // source rows per thread (two FFMA2 row pairs)
+constexpr int K1_ROWS_PER_WARP = 32 * K1_RPT; // 128
+constexpr int K1_ROWS = K1_THREADS * K1_RPT;  // 512 source rows per CTA
+constexpr int K1_TILE = 64;                   // target rows per pipeline stage
+constexpr int K1_STAGES = 4;
+constexpr int K1_JC = 8;                      // columns per register chunk
+
+struct __align__(128) K1Smem {
+    float b[K1_STAGES][K1_TILE][K1_D];        // 4 x 8 KB target tiles
+    float hb[K1_STAGES][K1_TILE];             // -|b_j|^2/2 of the tile's columns
+    uint64_t full[K1_STAGES];
+    uint64_t empty[K1_STAGES];
+};
+
+// ---- prep: half squared norms into the padded workspace (-inf in the padding) and zeroed packed bests ------------
+__global__ void __launch_bounds__(256) k1_prep_kernel(const float* __restrict__ x, const int32_t* __restrict__ off, int P, int D, int pad,
+                                                      float* __restrict__ hn, unsigned long long* __restrict__ packed)
+{
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)P * pad) return;
+    const int p = (int)(gid / pad), i = (int)(gid % pad);
+    const int o = off[p], n = off[p + 1] - o;
+    float h = -INFINITY;
+    if (i < n) {
+        const float* row = x + (size_t)(o + i) * D;
+        float s = 0.0f;
+        if ((D & 3) == 0) {
+            for (int k = 0; k < D; k += 4) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(row + k));
+                s = __fmaf_rn(v.x, v.x, s); s = __fmaf_rn(v.y, v.y, s); s = __fmaf_rn(v.z, v.z, s); s = __fmaf_rn(v.w, v.w, s);
+            }
+        } else {
+            for (int k = 0; k < D; ++k) { const float v = __ldg(row + k); s = __fmaf_rn(v, v, s); }
+        }
+        h = __fmul_rn(-0.5f, s);
+    }
+    hn[gid] = h;
+    packed[gid] = 0ull;
+}
+
+// ---- main kernel ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K1_THREADS, 2)
+k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
+                    const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
+                    const float* __restrict__ hna, const float* __restrict__ hnb, int padM, int padN,
+                    unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_packed, int splits)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    K1Smem& sm = *reinterpret_cast<K1Smem*>(smem_raw);
+
+    const int p = blockIdx.z;
+    const int so = src_off[p], M = src_off[p + 1] - so;
+    const int to = tgt_off[p], N = tgt_off[p + 1] - to;
+    const int row0 = blockIdx.x * K1_ROWS;
+    if (row0 >= M || N <= 0) return;
+    const int ntiles = (N + K1_TILE - 1) / K1_TILE;
+    const int t_begin = (int)(((long long)blockIdx.y * ntiles) / splits);
+    const int t_end = (int)(((long long)(blockIdx.y + 1) * ntiles) / splits);
+    if (t_begin >= t_end) return;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int active_warps = min(K1_WARPS, (M - row0 + K1_ROWS_PER_WARP - 1) / K1_ROWS_PER_WARP);
+
+    // zero the ring once so that rows a partial tile does not overwrite stay finite
+    for (int i = threadIdx.x; i < K1_STAGES * K1_TILE * K1_D / 4; i += K1_THREADS)
+        reinterpret_cast<float4*>(&sm.b[0][0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < K1_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], active_warps); }
+        mbar_fence_init();
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (warp >= active_warps) return;
+
+    const float* tgt_p = tgt + (size_t)to * K1_D;
+    const float* hnb_p = hnb + (size_t)p * padN;
+    auto issue_tile = [&](int t, int stage) {
+        const int nrows = min(K1_TILE, N - t * K1_TILE);
+        mbar_expect_tx(&sm.full[stage], (uint32_t)(nrows * K1_D * 4 + K1_TILE * 4));
+        tma_load_1d(&sm.b[stage][0][0], tgt_p + (size_t)t * K1_TILE * K1_D, (uint32_t)(nrows * K1_D * 4), &sm.full[stage]);
+        tma_load_1d(&sm.hb[stage][0], hnb_p + (size_t)t * K1_TILE, (uint32_t)(K1_TILE * 4), &sm.full[stage]);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < K1_STAGES && t_begin + s < t_end; ++s) issue_tile(t_begin + s, s);
+
+    // ---- this thread's 4 source rows, packed as two row pairs (stationary for the whole kernel) ------------------
+    const int i0 = row0 + warp * K1_ROWS_PER_WARP + lane * K1_RPT;
+    f32x2 ap[2][K1_D];
+#pragma unroll
+    for (int rp = 0; rp < 2; ++rp) {
+        const int ia = i0 + 2 * rp, ib = ia + 1;
+        const float4* ra = reinterpret_cast<const float4*>(src + (size_t)(so + ia) * K1_D);
+        const float4* rb = reinterpret_cast<const float4*>(src + (size_t)(so + ib) * K1_D);
+#pragma unroll
+        for (int k4 = 0; k4 < K1_D / 4; ++k4) {
+            const float4 x = (ia < M) ? __ldg(ra + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 y = (ib < M) ? __ldg(rb + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ap[rp][4 * k4 + 0] = pack2(x.x, y.x); ap[rp][4 * k4 + 1] = pack2(x.y, y.y);
+            ap[rp][4 * k4 + 2] = pack2(x.z, y.z); ap[rp][4 * k4 + 3] = pack2(x.w, y.w);
+        }
+    }
+    const float* hna_p = hna + (size_t)p * padM;
+    const float ha0 = hna_p[i0], ha1 = hna_p[i0 + 1], ha2 = hna_p[i0 + 2], ha3 = hna_p[i0 + 3];   // -inf beyond M
+    const f32x2 hap0 = pack2(ha0, ha1), hap1 = pack2(ha2, ha3);
+
+    float rbest[K1_RPT]; int ridx[K1_RPT];
+#pragma unroll
+    for (int r = 0; r < K1_RPT; ++r) { rbest[r] = -INFINITY; ridx[r] = 0; }
+    unsigned long long* colp = col_packed + (size_t)p * padN;
+
+    for (int t = t_begin; t < t_end; ++t) {
+        const int it = t - t_begin, stage = it % K1_STAGES;
+        const uint32_t phase = (uint32_t)(it / K1_STAGES) & 1u;
+        // producer: refill the stage the previous tile used (all warps have normally left it by now)
+        if (threadIdx.x == 0 && it >= 1 && t - 1 + K1_STAGES < t_end) {
+            const int ps = (it - 1) % K1_STAGES;
+            mbar_wait(&sm.empty[ps], (uint32_t)((it - 1) / K1_STAGES) & 1u);
+            issue_tile(t - 1 + K1_STAGES, ps);
+        }
+        __syncwarp();
+        mbar_wait(&sm.full[stage], phase);
+        const int ncols = min(K1_TILE, N - t * K1_TILE);
+        const int col0 = t * K1_TILE;
+
+#pragma unroll 1
+        for (int j0 = 0; j0 < ncols; j0 += K1_JC) {
+            f32x2 acc[2][K1_JC];
+            {
+                const float4 h0 = *reinterpret_cast<const float4*>(&sm.hb[stage][j0]);
+                const float4 h1 = *reinterpret_cast<const float4*>(&sm.hb[stage][j0 + 4]);
+                const float hb[K1_JC] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w };
+#pragma unroll
+                for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = pack2(hb[jj], hb[jj]); acc[1][jj] = acc[0][jj]; }
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < K1_D / 4; ++k4) {
+#pragma unroll
+                for (int jj = 0; jj < K1_JC; ++jj) {
+                    const float4 b = *reinterpret_cast<const float4*>(&sm.b[stage][j0 + jj][4 * k4]);   // warp-uniform address
+                    acc[0][jj] = fma2(ap[0][4 * k4 + 0], pack2(b.x, b.x), acc[0][jj]);
+                    acc[1][jj] = fma2(ap[1][4 * k4 + 0], pack2(b.x, b.x), acc[1][jj]);
+                    acc[0][jj] = fma2(ap[0][4 * k4 + 1], pack2(b.y, b.y), acc[0][jj]);
+                    acc[1][jj] = fma2(ap[1][4 * k4 + 1], pack2(b.y, b.y), acc[1][jj]);
+                    acc[0][jj] = fma2(ap[0][4 * k4 + 2], pack2(b.z, b.z), acc[0][jj]);
+                    acc[1][jj] = fma2(ap[1][4 * k4 + 2], pack2(b.z, b.z), acc[1][jj]);
+                    acc[0][jj] = fma2(ap[0][4 * k4 + 3], pack2(b.w, b.w), acc[0][jj]);
+                    acc[1][jj] = fma2(ap[1][4 * k4 + 3], pack2(b.w, b.w), acc[1][jj]);
+                }
+            }
+            // ---- row direction: value-only chunk maximum, index recovered only on improvement ---------------------
+            float v[K1_RPT][K1_JC];
+#pragma unroll
+            for (int jj = 0; jj < K1_JC; ++jj) { unpack2(acc[0][jj], v[0][jj], v[1][jj]); unpack2(acc[1][jj], v[2][jj], v[3][jj]); }
+#pragma unroll
+            for (int r = 0; r < K1_RPT; ++r) {
+                const float m = fmaxf(max3(v[r][0], v[r][1], v[r][2]), max3(v[r][3], v[r][4], max3(v[r][5], v[r][6], v[r][7])));
+                if (m > rbest[r]) {
+                    int sel = K1_JC - 1;
+#pragma unroll
+                    for (int jj = K1_JC - 2; jj >= 0; --jj) sel = (v[r][jj] == m) ? jj : sel;
+                    rbest[r] = m; ridx[r] = col0 + j0 + sel;
+                }
+            }
+            // ---- column direction: add -|a_i|^2/2, one warp-wide max per column, winner publishes ------------------
+#pragma unroll
+            for (int jj = 0; jj < K1_JC; ++jj) {
+                if (j0 + jj < ncols) {
+                    float t0, t1, t2, t3;
+                    unpack2(add2(acc[0][jj], hap0), t0, t1);
+                    unpack2(add2(acc[1][jj], hap1), t2, t3);
+                    const float m = fmaxf(max3(t0, t1, t2), t3);
+                    const float wm = warp_max(m);
+                    if (m == wm) {
+                        const int r = (t0 == wm) ? 0 : (t1 == wm) ? 1 : (t2 == wm) ? 2 : 3;
+                        atomicMax(colp + col0 + j0 + jj, pack_best(float_key(wm), (uint32_t)(i0 + r)));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+    }
+    unsigned long long* rowp = row_packed + (size_t)p * padM;
+#pragma unroll
+    for (int r = 0; r < K1_RPT; ++r)
+        if (i0 + r < M) atomicMax(rowp + i0 + r, pack_best(float_key(rbest[r]), (uint32_t)ridx[r]));
+}
+
+// ---- select: decode packed bests, mutual check, ascending compaction, optional gather of matched keypoints --------
+// One CTA per pair.  Mirrors models/BUFFER.py:356-357 (s_mids ascending, t_mids = nn_s[s_mids]) and :284,:287
+// (ss_kpts = kpts1[s_mids], tt_kpts = kpts2[t_mids]) written as 8-float records {sx sy sz 0 qx qy qz 0}.
+__global__ void __launch_bounds__(256) k1_select_kernel(const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
+                                                        const unsigned long long* __restrict__ row_packed, const unsigned long long* __restrict__ col_packed,
+                                                        const float* __restrict__ hna, int padM, int padN,
+                                                        int64_t* __restrict__ nn_s, int64_t* __restrict__ nn_t, float* __restrict__ d_s, float* __restrict__ d_t,
+                                                        const float* __restrict__ src_xyz, const float* __restrict__ tgt_xyz,
+                                                        int64_t* __restrict__ s_mids, int64_t* __restrict__ t_mids, int32_t* __restrict__ n_mutual,
+                                                        float4* __restrict__ corr)
+{
+    __shared__ int warp_cnt[8];
+    __shared__ int base_s;
+    const int p = blockIdx.x;
+    const int so = src_off[p], M = src_off[p + 1] - so, to = tgt_off[p], N = tgt_off[p + 1] - to;
+    const unsigned long long* rowp = row_packed + (size_t)p * padM;
+    const unsigned long long* colp = col_packed + (size_t)p * padN;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const unsigned long long c = colp[j];
+        if (nn_t) nn_t[to + j] = (int64_t)packed_index(c);
+        if (d_t) { const float d2 = __fmul_rn(-2.0f, key_float((uint32_t)(c >> 32))); d_t[to + j] = __fsqrt_rn(d2 > 0.0f ? d2 : 0.0f); }
+    }
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < M; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        bool flag = false; uint32_t j = 0;
+        if (i < M) {
+            const unsigned long long r = rowp[i];
+            j = packed_index(r);
+            if (nn_s) nn_s[so + i] = (int64_t)j;
+            if (d_s) { const float d2 = __fmul_rn(-2.0f, __fadd_rn(key_float((uint32_t)(r >> 32)), hna[(size_t)p * padM + i])); d_s[so + i] = __fsqrt_rn(d2 > 0.0f ? d2 : 0.0f); }
+            flag = (N > 0) && (j < (uint32_t)N) && (packed_index(colp[j]) == (uint32_t)i);
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int pre = base_s, tot = 0;
+        for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; if (w < warp) pre += c; tot += c; }
+        if (flag) {
+            const int pos = pre + __popc(bal & ((1u << lane) - 1u));
+            if (s_mids) { s_mids[so + pos] = (int64_t)i; t_mids[so + pos] = (int64_t)j; }
+            if (corr) {
+                const float* s = src_xyz + (size_t)(so + i) * 3; const float* q = tgt_xyz + (size_t)(to + j) * 3;
+                corr[2 * (size_t)(so + pos)] = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), 0.0f);
+                corr[2 * (size_t)(so + pos) + 1] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.0f);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base_s += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && n_mutual) n_mutual[p] = base_s;
+}
+
+// gather correspondences given explicit index pairs (the Open3D-style API: pcd0, pcd1, corr)
+__global__ void gather_corr_kernel(const float* __restrict__ src_xyz, const float* __restrict__ tgt_xyz, const int64_t* __restrict__ s_ids,
+                                   const int64_t* __restrict__ t_ids, int K, float4* __restrict__ corr)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    const float* s = src_xyz + (size_t)s_ids[c] * 3; const float* q = tgt_xyz + (size_t)t_ids[c] * 3;
+    corr[2 * (size_t)c] = make_float4(__ldg(s), __ldg(s + 1), __ldg(s + 2), 0.0f);
+    corr[2 * (size_t)c + 1] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.0f);
+}
+
+// ---- host launchers -------------------------------------------------------------------------------------------
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+int k1_pad_rows(int max_rows) { return round_up(max_rows > 0 ? max_rows : 1, K1_ROWS); }   // multiple of 512 (and of 64)
+
+size_t k1_workspace_bytes(int P, int max_M, int max_N)
+{
+    const size_t padM = (size_t)k1_pad_rows(max_M), padN = (size_t)k1_pad_rows(max_N);
+    return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long)) + 256;
+}
+
+cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N, int D,
+                      int col_splits, void* ws, int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t,
+                      const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr,
+                      cudaStream_t stream)
+{
+    if (D != K1_D) return cudaErrorInvalidValue;
+    const int padM = k1_pad_rows(max_M), padN = k1_pad_rows(max_N);
+    // workspace carve-up: packed u64 arrays first (8-byte aligned), then the float arrays (256-byte aligned for TMA)
+    unsigned char* w = reinterpret_cast<unsigned char*>(ws);
+    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    unsigned long long* row_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * padM * 8;
+    unsigned long long* col_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * padN * 8;
+    float* hna = reinterpret_cast<float*>(w); w += (size_t)P * padM * 4;
+    float* hnb = reinterpret_cast<float*>(w);
+
+    {
+        const long long na = (long long)P * padM, nb = (long long)P * padN;
+        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed);
+        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed);
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k1_mutual_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (col_splits < 1) col_splits = 1;
+    dim3 grid((unsigned)((max_M + K1_ROWS - 1) / K1_ROWS), (unsigned)col_splits, (unsigned)P);
+    if (max_M > 0 && max_N > 0)
+        k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);
+    k1_select_kernel<<<P, 256, 0, stream>>>(src_off, tgt_off, row_packed, col_packed, hna, padM, padN, nn_s, nn_t, d_s, d_t,
+                                            src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, reinterpret_cast<float4*>(corr));
+    return cudaGetLastError();
+}
+
+cudaError_t gather_corr_launch(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr, cudaStream_t stream)
+{
+    if (K > 0) gather_corr_kernel<<<(K + 255) / 256, 256, 0, stream>>>(src_xyz, tgt_xyz, s_ids, t_ids, K, reinterpret_cast<float4*>(corr));
+    return cudaGetLastError();
+}
+
+}  // namespace bfr

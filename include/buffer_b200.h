@@ -1,0 +1,120 @@
+/*
+ * buffer_b200.h — C ABI of libbuffer_b200.so: the B200-native (sm_100a) correspondence-and-pose back end of BUFFER.
+ *
+ * This is the drop-in boundary.  The reference (The-Learning-And-Vision-Atelier-LAVA/BUFFER) has no FFI layer of its
+ * own for this path — callers reach it through Python attribute lookup — so every entry point below names the
+ * reference symbol (file:line under /root/reference) whose work it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no torch / C++ types.  `stream` is a cudaStream_t passed as void*.
+ *  - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory including the
+ *    workspace (`ws`, size from the matching *_workspace_bytes); the library never allocates device memory, keeps no
+ *    per-call global state, and every call is asynchronous on `stream` (no host sync inside) unless stated.
+ *  - Batches are "varlen": pair p owns rows [off[p], off[p+1]) of the concatenated arrays; offsets are int32 DEVICE
+ *    arrays of P+1 entries; max_M / max_N are host-side upper bounds of the per-pair row counts (grid sizing).
+ *  - Row-major float32 everywhere.  Descriptor / keypoint base pointers must be 16-byte aligned (TMA bulk copies).
+ *  - Return value: 0 = ok; negative = argument error (BFR_E_*); positive = cudaError_t of the failing launch.
+ *    No exception crosses the ABI.  Failure convention of the path itself follows the reference: fewer than three
+ *    correspondences or no valid hypothesis yields the identity transform (ThreeDMatch/test.py:242-245).
+ *  - Correspondence records ("corr") are 8 floats per correspondence: sx sy sz w | qx qy qz 0 (w unused by RANSAC).
+ */
+#ifndef BUFFER_B200_H
+#define BUFFER_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFR_OK 0
+#define BFR_E_NULL (-1)      /* required pointer is NULL */
+#define BFR_E_SIZE (-2)      /* negative / inconsistent size */
+#define BFR_E_DIM (-3)       /* unsupported descriptor length (this build: D == 32) */
+#define BFR_E_WORKSPACE (-4) /* workspace too small */
+#define BFR_E_ALIGN (-5)     /* pointer not 16-byte aligned */
+
+int bfr_version(void);
+const char* bfr_error_string(int code);
+
+/* ---- K1: fused L2 distance + mutual nearest neighbour -------------------------------------------------------------
+ * Replaces buffer.mutual_matching (models/BUFFER.py:335-359) and its two knn_cuda.KNN(k=1) calls (:347, :352).
+ * Outputs (each optional, may be NULL): nn_s[i] = nearest tgt row of src row i, nn_t[j] = nearest src row of tgt row
+ * j (pair-local indices, int64 like knn_cuda); dist_* = Euclidean distances; s_mids/t_mids = the mutual matches of pair
+ * p, ascending in s, written at s_mids[src_off[p] ...] with n_mutual[p] entries (models/BUFFER.py:356-357); corr_xyz =
+ * the matched keypoints gathered into correspondence records at the same offsets (models/BUFFER.py:284,287; needs
+ * src_xyz/tgt_xyz [rows][3]).  col_splits >= 1 splits the target rows of each pair over that many CTAs (use > 1 when P
+ * is too small to fill 148 SMs). */
+size_t bfr_mutual_nn_workspace_bytes(int P, int max_M, int max_N);
+int bfr_mutual_matching_batched(const float* src_des, const float* tgt_des, const int32_t* src_off, const int32_t* tgt_off,
+                                int P, int max_M, int max_N, int D, int col_splits,
+                                int64_t* nn_s, int64_t* nn_t, float* dist_s, float* dist_t,
+                                const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr_xyz,
+                                void* ws, size_t ws_bytes, void* stream);
+
+/* Gather explicit index pairs into correspondence records: the (pcd0, pcd1, corr) arguments of the Open3D call at
+ * models/BUFFER.py:314-316.  s_ids/t_ids: int64 [K]. */
+int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr_xyz, void* stream);
+
+/* ---- K2 + K3: RANSAC (Philox sampling, 3-point Kabsch, checkers, inlier scoring, packed max) ---------------------------
+ * Replaces o3d.pipelines.registration.registration_ransac_based_on_correspondence as called at models/BUFFER.py:318-324
+ * (ransac_n = 3, point-to-point without scaling, edge-length checker `similar_th`, distance checker `dist_th`,
+ * max_correspondence_distance = dist_th).  Evaluates hypotheses [h_begin, h_end) of every pair — hypothesis h of pair p
+ * draws Philox4x32-10(key = seed, counter = (h, pair_id_base + p, 0, 0)) — and max-accumulates into best_packed[p] =
+ * (inlier count << 32) | (0xFFFFFFFF - h): the caller zeroes best_packed before the first call and may split the
+ * hypothesis range over several calls, streams or GPUs (all-reduce MAX) before finalising.  corr_cnt[p] < 3 leaves 0. */
+int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
+                       uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
+                       float dist_th, float similar_th, int splits, uint64_t* best_packed, void* stream);
+/* Decode best_packed and regenerate the winning minimal-sample fit: T [P][16] row-major 4x4 (result.transformation,
+ * models/BUFFER.py:326), inlier count and hypothesis index (-1 if none; T = identity). */
+int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
+                                uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th, const uint64_t* best_packed,
+                                float* T, int32_t* inliers, int64_t* best_h, void* stream);
+
+/* ---- a3 / a4: per-correspondence LRF hypotheses and their scoring --------------------------------------------------
+ * bfr_lrf_hypotheses replaces models/BUFFER.py:294-301: R = tt_R Rz(angle) ss_R^T, t = tt_kpts - R ss_kpts; cs[i] =
+ * {cos(angle_i), sin(angle_i)} is supplied by the caller.  bfr_score_hypotheses replaces models/BUFFER.py:303-311:
+ * counts[h] = #{c : |R_h s_c + t_h - q_c| < thr_c}; best_idx = first maximum (torch.argmax); mask = inliers of the
+ * best.  thr: [C] per-correspondence thresholds or NULL (then thr_scalar). */
+int bfr_lrf_hypotheses(const float* cs, const float* ss_R, const float* tt_R, const float* ss_kpts, const float* tt_kpts, int A,
+                       float* R_out, float* t_out, void* stream);
+size_t bfr_score_workspace_bytes(int C);
+int bfr_score_hypotheses(const float* R, const float* t, int H, const float* src, const float* tgt, int C, const float* thr, float thr_scalar,
+                         int32_t* counts, uint64_t* best_packed, int64_t* best_idx, uint8_t* mask, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- K4: weighted Kabsch and post-refinement ------------------------------------------------------------------------
+ * bfr_rigid_transform_3d replaces rigid_transform_3d (models/BUFFER.py:424-464): A, B [bs][n][3], w [bs][n] or NULL,
+ * T [bs][16].  bfr_post_refinement_batched replaces buffer.post_refinement (models/BUFFER.py:382-418) for P pairs:
+ * T0/T_out [P][16]; thr = 0.10 (3DMatch/3DLoMatch/ETH) or 1.2 (KITTI), max_iter = 20 in the reference. */
+int bfr_rigid_transform_3d(const float* A, const float* B, const float* w, int bs, int n, float weight_threshold, float* T, void* stream);
+int bfr_post_refinement_batched(const float* T0, const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
+                                float thr, int max_iter, float* T_out, int32_t* iters, int32_t* inliers, void* stream);
+
+/* ---- whole back end: descriptors + keypoints -> pose, one call, no host sync -----------------------------------------
+ * The test branch of buffer.forward after the descriptors exist, without the learned inlier head:
+ * mutual_matching (:283) -> gather (:284-287) -> RANSAC on all mutual matches (:313-326) -> post_refinement (:327-329).
+ * refine_iters = 0 skips refinement (KITTI config, pose_refine=False).  total_M/total_N = rows of the concatenated arrays. */
+size_t bfr_register_workspace_bytes(int P, int max_M, int max_N, int total_M, int total_N);
+int bfr_register_batched(const float* src_des, const float* src_xyz, const int32_t* src_off,
+                         const float* tgt_des, const float* tgt_xyz, const int32_t* tgt_off,
+                         int P, int max_M, int max_N, int total_M, int total_N, int D,
+                         int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th,
+                         float refine_thr, int refine_iters, int ransac_splits,
+                         float* T_out, int32_t* n_mutual, int32_t* n_inliers, void* ws, size_t ws_bytes, void* stream);
+
+/* Same, for a uniform batch (every pair has M source and N target rows) whose inputs live in HOST memory (pinned for
+ * truly asynchronous copies): copies inputs host->device on `stream`, runs the back end, copies T / n_mutual /
+ * n_inliers back to host buffers.  Still asynchronous: the caller synchronises `stream` before reading the outputs.
+ * The device staging area is part of `ws` (bfr_register_host_workspace_bytes). */
+size_t bfr_register_host_workspace_bytes(int P, int M, int N, int D);
+int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_host, const float* tgt_des_host, const float* tgt_xyz_host,
+                              int P, int M, int N, int D, int hypotheses, uint64_t seed, uint32_t pair_id_base,
+                              float dist_th, float similar_th, float refine_thr, int refine_iters, int ransac_splits,
+                              float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BUFFER_B200_H */

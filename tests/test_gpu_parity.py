@@ -1,0 +1,231 @@
+"""GPU parity tests proper: every result of the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Integer / index / count outputs must be bit-exact; transforms are compared bit-for-bit where the
+arithmetic order is pinned (RANSAC fit, refinement) and within 1e-5 against float64 ground truth otherwise."""
+import numpy as np
+import pytest
+import torch
+
+from buffer_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pairs(P, N, **kw):
+    return S.make_pairs(P, N, **kw)
+
+
+@pytest.mark.parametrize("M,N", [(1, 1), (3, 5), (64, 64), (65, 63), (511, 513), (512, 512), (700, 1300), (2500, 1500)])
+def test_mutual_nn_bit_exact_ragged(oracle, backend, M, N):
+    g = torch.Generator().manual_seed(M * 10007 + N)
+    src = torch.nn.functional.normalize(torch.randn(M, 32, generator=g), dim=-1)
+    tgt = torch.nn.functional.normalize(torch.randn(N, 32, generator=g), dim=-1)
+    if M > 10 and N > 10:           # plant duplicates -> exact distance ties, lowest index must win
+        tgt[7] = tgt[3]; src[9] = src[2]
+        k = min(M, N) // 2
+        tgt[:k] = torch.nn.functional.normalize(src[:k] + 0.05 * torch.randn(k, 32, generator=g), dim=-1)
+    nn_s, nn_t, ds, dt = oracle.mutual_nn(src.numpy(), tgt.numpy(), want_dist=True)
+    r = backend.mutual_matching_device(src.to(DEV), tgt.to(DEV), want_dist=True)
+    assert np.array_equal(r["nn_s"].cpu().numpy(), nn_s)
+    assert np.array_equal(r["nn_t"].cpu().numpy(), nn_t)
+    assert np.array_equal(r["dist_s"].cpu().numpy(), ds)
+    assert np.array_equal(r["dist_t"].cpu().numpy(), dt)
+    s, t = oracle.mutual_select(nn_s, nn_t)
+    n = int(r["n_mutual"].item())
+    assert n == len(s)
+    assert np.array_equal(r["s_mids"][:n].cpu().numpy(), s) and np.array_equal(r["t_mids"][:n].cpu().numpy(), t)
+    s2, t2 = backend.mutual_matching(src.to(DEV), tgt.to(DEV))
+    assert s2.dtype == np.int64 and np.array_equal(s2, s) and np.array_equal(t2, t)
+
+
+def test_mutual_nn_unnormalised_and_splits(oracle, backend):
+    g = torch.Generator().manual_seed(5)
+    src = torch.randn(900, 32, generator=g) * torch.rand(900, 1, generator=g) * 3
+    tgt = torch.randn(1100, 32, generator=g) * torch.rand(1100, 1, generator=g) * 3
+    nn_s, nn_t = oracle.mutual_nn(src.numpy(), tgt.numpy())
+    so = torch.tensor([0, 900], dtype=torch.int32, device=DEV); to = torch.tensor([0, 1100], dtype=torch.int32, device=DEV)
+    for splits in (1, 2, 5, 18):
+        r = backend.mutual_matching_batched(src.to(DEV), tgt.to(DEV), so, to, 900, 1100, col_splits=splits)
+        assert np.array_equal(r["nn_s"].cpu().numpy(), nn_s), splits
+        assert np.array_equal(r["nn_t"].cpu().numpy(), nn_t), splits
+
+
+def test_mutual_matching_batched_varlen(oracle, backend):
+    sizes = [(300, 200), (1, 7), (1025, 513), (64, 640), (5, 5)]
+    g = torch.Generator().manual_seed(11)
+    srcs = [torch.nn.functional.normalize(torch.randn(m, 32, generator=g), dim=-1) for m, _ in sizes]
+    tgts = [torch.nn.functional.normalize(torch.randn(n, 32, generator=g), dim=-1) for _, n in sizes]
+    sx = [torch.randn(m, 3, generator=g) for m, _ in sizes]; tx = [torch.randn(n, 3, generator=g) for _, n in sizes]
+    so = backend._offsets([m for m, _ in sizes], torch.device(DEV)); to = backend._offsets([n for _, n in sizes], torch.device(DEV))
+    r = backend.mutual_matching_batched(torch.cat(srcs).to(DEV), torch.cat(tgts).to(DEV), so, to, 1025, 640,
+                                        torch.cat(sx).to(DEV), torch.cat(tx).to(DEV))
+    torch.cuda.synchronize()
+    so_h = so.cpu().numpy(); to_h = to.cpu().numpy()
+    for p, (m, n) in enumerate(sizes):
+        nn_s, nn_t = oracle.mutual_nn(srcs[p].numpy(), tgts[p].numpy())
+        assert np.array_equal(r["nn_s"][so_h[p]:so_h[p + 1]].cpu().numpy(), nn_s)
+        assert np.array_equal(r["nn_t"][to_h[p]:to_h[p + 1]].cpu().numpy(), nn_t)
+        s, t = oracle.mutual_select(nn_s, nn_t)
+        k = int(r["n_mutual"][p].item())
+        assert k == len(s)
+        assert np.array_equal(r["s_mids"][so_h[p]:so_h[p] + k].cpu().numpy(), s)
+        corr = oracle.gather_corr(sx[p].numpy(), tx[p].numpy(), s, t)
+        assert np.array_equal(r["corr"][so_h[p]:so_h[p] + k].cpu().numpy()[:, [0, 1, 2, 4, 5, 6]], corr[:, [0, 1, 2, 4, 5, 6]])
+
+
+@pytest.mark.parametrize("N,H,rho", [(600, 4000, 0.7), (2500, 6000, 0.7), (1000, 20000, 0.93)])
+def test_ransac_counts_and_fit_bit_exact(oracle, backend, N, H, rho):
+    b = _pairs(3, N, cfg_id=7, outlier_ratio=rho)
+    seed = 0x1234ABCD5678
+    for p in range(3):
+        s, t = oracle.mutual_matching(b.src_des[p].numpy(), b.tgt_des[p].numpy())
+        corr = oracle.gather_corr(b.src_xyz[p].numpy(), b.tgt_xyz[p].numpy(), s, t)
+        best = oracle.ransac(corr, seed, 40 + p, H, 0.1, 0.8)
+        T_o, cnt_o, bh_o = oracle.ransac_finalize(corr, seed, 40 + p, best, 0.1, 0.8)
+        cd = torch.from_numpy(corr).to(DEV)
+        off = torch.tensor([0, len(s)], dtype=torch.int32, device=DEV); cnt = torch.tensor([len(s)], dtype=torch.int32, device=DEV)
+        for splits in (1, 7):
+            bp = backend.ransac_batched(cd, off, cnt, H, 0.1, 0.8, seed=seed, pair_id_base=40 + p, splits=splits)
+            assert int(bp.item()) == best, (p, splits)
+        T, inl, bh = backend.ransac_finalize_batched(cd, off, cnt, bp, 0.1, 0.8, seed=seed, pair_id_base=40 + p)
+        assert int(inl.item()) == cnt_o and int(bh.item()) == bh_o
+        assert np.array_equal(T[0].cpu().numpy(), T_o)            # same closed-form fit, bit for bit
+        # split the hypothesis range over two calls (the multi-GPU mode) -> same packed best
+        bp2 = backend.ransac_batched(cd, off, cnt, H, 0.1, 0.8, seed=seed, pair_id_base=40 + p, h_begin=0, h_end=H // 3)
+        bp2 = backend.ransac_batched(cd, off, cnt, H, 0.1, 0.8, seed=seed, pair_id_base=40 + p, h_begin=H // 3, h_end=H, best_packed=bp2)
+        assert int(bp2.item()) == best
+
+
+def test_ransac_degenerate_inputs(oracle, backend):
+    dev = torch.device(DEV)
+    for K in (0, 1, 2):
+        corr = torch.randn(max(K, 1), 8, device=dev)
+        off = torch.tensor([0, K], dtype=torch.int32, device=dev); cnt = torch.tensor([K], dtype=torch.int32, device=dev)
+        bp = backend.ransac_batched(corr, off, cnt, 1000, 0.1, 0.8)
+        T, inl, bh = backend.ransac_finalize_batched(corr, off, cnt, bp, 0.1, 0.8)
+        assert int(bp.item()) == 0 and int(inl.item()) == 0 and int(bh.item()) == -1
+        assert torch.equal(T[0].cpu(), torch.eye(4))
+    # collinear / identical points: no valid hypothesis -> identity
+    corr = torch.zeros(50, 8, device=dev); corr[:, 0] = torch.arange(50, device=dev); corr[:, 4] = torch.arange(50, device=dev)
+    off = torch.tensor([0, 50], dtype=torch.int32, device=dev); cnt = torch.tensor([50], dtype=torch.int32, device=dev)
+    bp = backend.ransac_batched(corr, off, cnt, 2000, 0.1, 0.8)
+    assert int(bp.item()) == oracle.ransac(corr.cpu().numpy(), 0, 0, 2000, 0.1, 0.8)
+
+
+def test_open3d_style_call(oracle, backend):
+    b = _pairs(1, 800, cfg_id=9)
+    s, t = oracle.mutual_matching(b.src_des[0].numpy(), b.tgt_des[0].numpy())
+    keep = np.arange(0, len(s), 2)
+    corr_idx = np.stack([s[keep], t[keep]], 1)
+    res = backend.registration_ransac_based_on_correspondence(b.src_xyz[0].to(DEV), b.tgt_xyz[0].to(DEV), corr_idx, 0.1, 0.8, iter_n=5000,
+                                                              confidence=0.999, seed=3, pair_id=1)
+    corr = oracle.gather_corr(b.src_xyz[0].numpy(), b.tgt_xyz[0].numpy(), s[keep], t[keep])
+    best = oracle.ransac(corr, 3, 1, 5000, 0.1, 0.8)
+    T_o, cnt_o, _ = oracle.ransac_finalize(corr, 3, 1, best, 0.1, 0.8)
+    assert res.transformation.dtype == np.float64 and res.transformation.shape == (4, 4)
+    assert np.array_equal(res.transformation.astype(np.float32), T_o) and res.inlier_count == cnt_o
+    res0 = backend.registration_ransac_based_on_correspondence(b.src_xyz[0].to(DEV), b.tgt_xyz[0].to(DEV), corr_idx[:2], 0.1, 0.8, iter_n=100)
+    assert np.array_equal(res0.transformation, np.eye(4))
+
+
+def test_lrf_hypotheses_and_scoring_bit_exact(oracle, backend):
+    A = 700
+    g = torch.Generator().manual_seed(21)
+    ss_R = S.quat_to_rot(torch.randn(A, 4, generator=g)); ind = torch.rand(A, generator=g) * 20
+    Rg = S.quat_to_rot(torch.randn(1, 4, generator=g))[0]; tg = torch.rand(3, generator=g)
+    ss = torch.rand(A, 3, generator=g) * 3 - 1.5
+    tt = ss @ Rg.T + tg + 0.01 * torch.randn(A, 3, generator=g)
+    ang = ind.double() * 2 * np.pi / 20 + 1e-6
+    Rz = torch.zeros(A, 3, 3, dtype=torch.float64); Rz[:, 0, 0] = torch.cos(ang); Rz[:, 0, 1] = -torch.sin(ang)
+    Rz[:, 1, 0] = torch.sin(ang); Rz[:, 1, 1] = torch.cos(ang); Rz[:, 2, 2] = 1
+    tt_R = (Rg.double() @ ss_R.double() @ Rz.transpose(-1, -2)).float()      # so that tt_R Rz ss_R^T = Rg for true matches
+    out = torch.rand(A, generator=g) < 0.6
+    tt[out] = torch.rand(int(out.sum()), 3, generator=g) * 3
+    tt_R[out] = S.quat_to_rot(torch.randn(int(out.sum()), 4, generator=g))
+    cs = torch.stack([torch.cos(ang), torch.sin(ang)], -1).float()
+    R_o, t_o = oracle.lrf_hypotheses(cs.numpy(), ss_R.numpy(), tt_R.numpy(), ss.numpy(), tt.numpy())
+    R_g, t_g = backend.lrf_hypotheses(ind.to(DEV), ss_R.to(DEV), tt_R.to(DEV), ss.to(DEV), tt.to(DEV))
+    assert np.array_equal(R_g.cpu().numpy(), R_o) and np.array_equal(t_g.cpu().numpy(), t_o)
+    thr = backend.inlier_threshold(ss)
+    for th in (thr, 0.08):
+        c_o, b_o, m_o = oracle.score_hypotheses(R_o, t_o, ss.numpy(), tt.numpy(), th if np.isscalar(th) else th.numpy())
+        c_g, b_g, m_g = backend.score_hypotheses(R_g, t_g, ss.to(DEV), tt.to(DEV), th if np.isscalar(th) else th.to(DEV))
+        assert np.array_equal(c_g.cpu().numpy(), c_o) and int(b_g.item()) == b_o and np.array_equal(m_g.cpu().numpy(), m_o)
+    assert c_o.max() > 0.25 * A
+
+
+@pytest.mark.parametrize("bs,n", [(1, 3), (4, 3), (2, 50), (3, 257), (1, 5000)])
+def test_rigid_transform_3d_bit_exact(oracle, backend, bs, n):
+    g = torch.Generator().manual_seed(bs * 100 + n)
+    A = torch.randn(bs, n, 3, generator=g); Rg = S.quat_to_rot(torch.randn(bs, 4, generator=g)); tg = torch.randn(bs, 1, 3, generator=g)
+    B = A @ Rg.transpose(-1, -2) + tg + 0.01 * torch.randn(bs, n, 3, generator=g)
+    w = torch.rand(bs, n, generator=g)
+    for weights, thr in ((None, 0), (w, 0), (w, 0.3)):
+        To = oracle.rigid_transform_3d(A.numpy(), B.numpy(), None if weights is None else weights.numpy().copy(), thr)
+        wd = None if weights is None else weights.clone().to(DEV)
+        Tg = backend.rigid_transform_3d(A.to(DEV), B.to(DEV), wd, thr)
+        assert np.array_equal(Tg.cpu().numpy(), To)
+        if weights is not None and thr > 0:
+            assert float(wd[wd < thr].abs().sum()) == 0.0          # in-place zeroing like the reference
+    # reflection case: mirrored target must still give a proper rotation
+    Bm = B.clone(); Bm[..., 0] = -Bm[..., 0]
+    Tm = backend.rigid_transform_3d(A.to(DEV), Bm.to(DEV)).cpu()
+    if n > 3:
+        assert torch.allclose(torch.det(Tm[:, :3, :3]), torch.ones(bs), atol=1e-5)
+
+
+def test_post_refinement_bit_exact(oracle, backend):
+    b = _pairs(4, 1500, cfg_id=13)
+    for p in range(4):
+        s, t = oracle.mutual_matching(b.src_des[p].numpy(), b.tgt_des[p].numpy())
+        corr = oracle.gather_corr(b.src_xyz[p].numpy(), b.tgt_xyz[p].numpy(), s, t)
+        T0 = b.T_gt[p].clone(); T0[:3, 3] += 0.03; T0 = T0.numpy()
+        To, it_o, inl_o = oracle.post_refinement(T0, corr, 0.10, 20)
+        Tg = backend.post_refinement(torch.from_numpy(T0)[None].to(DEV), torch.from_numpy(corr[:, 0:3])[None].to(DEV),
+                                     torch.from_numpy(corr[:, 4:7])[None].to(DEV))
+        assert Tg.shape == (1, 4, 4) and np.array_equal(Tg[0].cpu().numpy(), To)
+        assert it_o >= 1 and inl_o > 300
+
+
+def test_register_pipeline_matches_oracle_and_recovers_pose(oracle, backend):
+    P, N, H = 6, 1200, 8000
+    b = _pairs(P, N, cfg_id=17)
+    off = np.arange(P + 1, dtype=np.int32) * N
+    To, nm_o, ni_o = oracle.register_batched(b.src_des.reshape(-1, 32).numpy(), b.src_xyz.reshape(-1, 3).numpy(), off,
+                                             b.tgt_des.reshape(-1, 32).numpy(), b.tgt_xyz.reshape(-1, 3).numpy(), off, H, 99, 0, 0.1, 0.8, 0.1, 20)
+    bd = b.to(DEV)
+    T, nm, ni = backend.register_uniform(bd.src_des, bd.src_xyz, bd.tgt_des, bd.tgt_xyz, hypotheses=H, seed=99)
+    assert np.array_equal(nm.cpu().numpy(), nm_o) and np.array_equal(ni.cpu().numpy(), ni_o)
+    assert np.array_equal(T.cpu().numpy(), To)
+    recall, rte, rre = S.registration_recall(T.cpu(), b.T_gt)
+    assert recall == 1.0 and float(rte.max()) < 0.01 and float(rre.max()) < 0.5
+    # host-buffer entry point (pinned memory, two streams) gives the same poses
+    reg = backend.HostRegistrar(4, N, N, DEV, hypotheses=H, seed=99)
+    pin = lambda x: x.contiguous().pin_memory()
+    Th = torch.empty(P, 4, 4).pin_memory(); nmh = torch.empty(P, dtype=torch.int32).pin_memory()
+    reg.run(pin(b.src_des), pin(b.src_xyz), pin(b.tgt_des), pin(b.tgt_xyz), Th, nmh)
+    assert np.array_equal(Th.numpy(), To) and np.array_equal(nmh.numpy(), nm_o)
+
+
+def test_full_size_properties(backend):
+    """config-2-sized pairs (5000 keypoints, 50k hypotheses): size-independent properties instead of the slow oracle"""
+    P, N = 8, 5000
+    b = _pairs(P, N, cfg_id=2).to(DEV)
+    r = backend.mutual_matching_batched(b.src_des.reshape(-1, 32), b.tgt_des.reshape(-1, 32),
+                                        (torch.arange(P + 1, dtype=torch.int32) * N).to(DEV), (torch.arange(P + 1, dtype=torch.int32) * N).to(DEV), N, N)
+    nn_s = r["nn_s"].reshape(P, N); nn_t = r["nn_t"].reshape(P, N)
+    assert torch.equal(nn_s, b.perm)                                 # planted permutation recovered
+    assert torch.equal(torch.gather(nn_t, 1, nn_s), torch.arange(N, device=DEV).expand(P, N))
+    assert int(r["n_mutual"].min()) == N
+    sm = r["s_mids"].reshape(P, N)
+    assert bool((sm[:, 1:] > sm[:, :-1]).all())                      # ascending
+    T, nm, ni = backend.register_uniform(b.src_des, b.src_xyz, b.tgt_des, b.tgt_xyz, hypotheses=50000, seed=1)
+    T2, _, ni2 = backend.register_uniform(b.src_des, b.src_xyz, b.tgt_des, b.tgt_xyz, hypotheses=50000, seed=1, ransac_splits=5)
+    assert torch.equal(T, T2) and torch.equal(ni, ni2)               # deterministic, independent of the CTA split
+    recall, rte, rre = S.registration_recall(T.cpu(), b.T_gt.cpu())
+    assert recall == 1.0
+    assert float(rte.max()) < 2e-3 and float(S.rotation_error_rad(T[:, :3, :3].cpu(), b.T_gt[:, :3, :3].cpu()).max()) < 2e-3
+    assert int(ni.min()) > 0.27 * N                                  # ~30 % planted inliers found by the best hypothesis
+    R = T[:, :3, :3].double().cpu()
+    assert float((R @ R.transpose(-1, -2) - torch.eye(3, dtype=torch.float64)).abs().max()) < 1e-5
+    assert torch.allclose(torch.det(R), torch.ones(P, dtype=torch.float64), atol=1e-5)

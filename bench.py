@@ -1,0 +1,308 @@
+#!/usr/bin/env python3
+"""bench.py — fragment pairs/sec of the BUFFER correspondence-and-pose back end (match + RANSAC + SVD) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P] [--config 2]
+
+One "step" = one pass of the hot path (mutual-NN matching -> Philox RANSAC with 3-point Kabsch and inlier scoring ->
+weighted-Kabsch post-refinement) over one batch of synthetic fragment pairs.  Default workload = BASELINE.json
+configs[1]: 1,623 pairs x 5,000 keypoints x 32-d descriptors, 50,000 hypotheses per pair, 70 % outliers.
+N > 1 (torchrun): pairs are independent, every rank processes its own 1,623 pairs, no data-path collective (weak
+scaling); time = max over ranks.  Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md §bench).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from buffer_b200 import synthetic as S  # noqa: E402
+
+METRIC = "fragment_pairs_per_sec_match_ransac_svd"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config id (1-5); 2 is the one the metric is quoted on")
+    ap.add_argument("--pairs", type=int, default=0, help="override the number of pairs per GPU (0 = the config's)")
+    ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU baseline sample (0 = 4 per host thread)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload(cfg_id, pairs_override):
+    c = S.CONFIGS[cfg_id]
+    P = pairs_override or c["num_pairs"]
+    return c, P
+
+
+def gen_pairs(c, P, first_pair, device, chunk=128):
+    """generate P pairs in chunks (bounded temporary memory) -> PairBatch on `device`"""
+    parts = []
+    for p0 in range(0, P, chunk):
+        n = min(chunk, P - p0)
+        parts.append(S.make_pairs(n, first_pair=first_pair + p0, device=device, **c["gen"]))
+    cat = lambda f: torch.cat([getattr(b, f) for b in parts], 0)
+    return S.PairBatch(cat("src_des"), cat("tgt_des"), cat("src_xyz"), cat("tgt_xyz"), cat("T_gt"), cat("perm"), cat("inlier"))
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        pw = [float(r[2]) for r in self.rows if len(r) >= 7 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 7 and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def fp32_peak_tflops(dev):
+    """live FFMA2 issue peak on this GPU (bfr_fp32_probe), best of 5"""
+    from buffer_b200 import _lib
+    L = _lib.lib()
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    grid, iters = sms * 4, 4000
+    scratch = torch.full((grid * 256 + 128,), 1.0009765625, dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    best = 0.0
+    for _ in range(6):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(L.bfr_fp32_probe(grid, iters, scratch.data_ptr(), st), "bfr_fp32_probe")
+        e1.record(); e1.synchronize()
+        best = max(best, grid * 256.0 * iters * 64 * 4 / (e0.elapsed_time(e1) * 1e-3) * 1e-12)   # 64 FFMA2 = 256 flop / thread / iteration
+    return best
+
+
+def cpu_baseline(c, sample_pairs, threads, b=None):
+    """the oracle port (oracle/bfr_oracle.c, OpenMP over pairs) on the host cores, on a bounded sample of the workload
+    (`b`: the first pairs of the GPU workload copied to the host, else freshly generated ones)"""
+    from oracle import oracle as O
+    O.build()
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    if b is None:
+        b = S.make_pairs(sample_pairs, first_pair=0, **c["gen"])
+    N = c["gen"]["num_kpts"]
+    off = np.arange(sample_pairs + 1, dtype=np.int32) * N
+    args = (b.src_des.reshape(-1, 32).numpy(), b.src_xyz.reshape(-1, 3).numpy(), off, b.tgt_des.reshape(-1, 32).numpy(),
+            b.tgt_xyz.reshape(-1, 3).numpy(), off, c["hypotheses"], 0, 0, c["dist_th"], c["similar_th"], c["refine_thr"], 20)
+    t0 = time.perf_counter()
+    T, nm, ni = O.register_batched(*args)
+    dt = time.perf_counter() - t0
+    return sample_pairs / dt, dt, T, b
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is Python + third-party natives
+    that cannot travel to the GPU box, so this arm times the oracle port with all host threads (tier rule)."""
+    if rank != 0:
+        return
+    c, P = workload(args.config, args.pairs)
+    threads = os.cpu_count() or 1
+    sample = args.cpu_sample_pairs or max(threads * 2, 8)
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, _, _ = cpu_baseline(c, sample, threads)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    v = sum(sample for _ in vals) / sum(dt for _, dt in vals)
+    ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, c, P),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": "%d pairs of the workload per step (same generator, seeds 0..), whole back end" % sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, c, P):
+    return {"workload": "BASELINE.json configs[%d]: %d pairs/GPU x %d keypoints x 32-d, %d RANSAC hypotheses/pair, outlier ratio %s"
+                        % (args.config - 1, P, c["gen"]["num_kpts"], c["hypotheses"], c["gen"].get("outlier_ratio")),
+            "pairs_per_gpu": P, "keypoints": c["gen"]["num_kpts"], "desc_dim": 32, "hypotheses": c["hypotheses"],
+            "dist_th": c["dist_th"], "similar_th": c["similar_th"], "refine_iters": 20,
+            "cache": "inputs (%.2f GB/GPU) exceed the 126 MB L2; every step re-reads them from HBM" % (P * c["gen"]["num_kpts"] * 2 * (32 + 3) * 4 / 1e9),
+            "parallelism": "pairs sharded by rank, no collective in the data path"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from buffer_b200 import _lib, backend as B
+    L = _lib.lib()
+
+    c, P = workload(args.config, args.pairs)
+    N = c["gen"]["num_kpts"]
+    kw = dict(hypotheses=c["hypotheses"], dist_th=c["dist_th"], similar_th=c["similar_th"], refine_thr=c["refine_thr"], refine_iters=20, seed=0)
+    batch = gen_pairs(c, P, rank * P, dev)                       # resident in HBM before the timed region
+    src_des = batch.src_des.reshape(P * N, 32); tgt_des = batch.tgt_des.reshape(P * N, 32)
+    src_xyz = batch.src_xyz.reshape(P * N, 3); tgt_xyz = batch.tgt_xyz.reshape(P * N, 3)
+    off = (torch.arange(P + 1, dtype=torch.int32) * N).to(dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return B.register_batched(src_des, src_xyz, off, tgt_des, tgt_xyz, off, N, N, pair_id_base=rank * P, **kw)
+
+    peak_tf = fp32_peak_tflops(dev)
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    # ---- timed region: exactly K steps, device-timed, K1 bracketed by its own events ----------------------------
+    k1_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b_ in k1_ev:                      # torch creates events lazily: record once so the handles exist, the library re-records them
+        a.record(); b_.record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0.record()
+    for i in range(args.steps):
+        L.bfr_debug_set_k1_events(ctypes.c_void_p(k1_ev[i][0].cuda_event), ctypes.c_void_p(k1_ev[i][1].cuda_event))
+        out = step()
+    e1.record()
+    L.bfr_debug_set_k1_events(None, None)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    k1_ms = sum(a.elapsed_time(b) for a, b in k1_ev) / args.steps
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = world * P / (ms_step * 1e-3)
+    T, nm, ni = out
+    recall, rte, rre = S.registration_recall(T.cpu(), batch.T_gt.cpu())
+
+    # ---- e2e: host (pinned) buffers -> poses on the host, copies inside the timed region ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        hb = batch.to("cpu")
+        pin = lambda x: x.contiguous().pin_memory()
+        h = [pin(hb.src_des), pin(hb.src_xyz), pin(hb.tgt_des), pin(hb.tgt_xyz)]
+        Th = torch.empty(P, 4, 4).pin_memory(); nmh = torch.empty(P, dtype=torch.int32).pin_memory(); nih = torch.empty(P, dtype=torch.int32).pin_memory()
+        chunk = min(P, 256)
+        reg = B.HostRegistrar(chunk, N, N, dev, ransac_splits=None, **kw)
+        for _ in range(2):
+            reg.run(*h, Th, nmh, nih)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            reg.run(*h, Th, nmh, nih)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        same = bool(torch.equal(Th, T.cpu()))
+        e2e = {"value": world * P * args.steps / tt.item(), "unit": UNIT,
+               "h2d_bytes_per_step": int(sum(x.numel() * 4 for x in h)), "d2h_bytes_per_step": int(Th.numel() * 4 + nmh.numel() * 4 + nih.numel() * 4),
+               "api": "buffer_b200.backend.HostRegistrar.run -> bfr_register_uniform_host (pinned host buffers, %d-pair chunks on 2 streams)" % chunk,
+               "poses_equal_device_path": same, "launches_per_step": 8 * ((P + chunk - 1) // chunk)}
+
+    if rank == 0:
+        flops_k1 = 2.0 * N * N * 32 * P
+        ach = flops_k1 / (k1_ms * 1e-3) * 1e-12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, c, P), "clocks": clocks, "gpu_launches": 7 * args.steps,
+                "roofline": {"kernel": "k1_mutual_nn_kernel", "bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                             "traffic": traffic, "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step,
+                             "algorithmic_flops_per_launch": flops_k1,
+                             "peak_source": "live FFMA2 (fma.rn.f32x2) issue-rate probe on this GPU; MEASURED_PEAKS.json has no FP32 figure "
+                                            "(theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s)",
+                             "hbm_peak_gbs_measured": _measured_hbm()},
+                "quality": {"registration_recall": recall, "rte_max_m": float(rte.max()), "rre_max_deg": float(rre.max()),
+                            "mutual_matches_mean": float(nm.float().mean()), "ransac_inliers_mean": float(ni.float().mean())}}
+        if e2e is not None:
+            line["e2e"] = e2e
+        if not args.no_cpu:
+            threads = os.cpu_count() or 1
+            sample = min(P, args.cpu_sample_pairs or max(threads * 4, 8))
+            hs = S.PairBatch(*[getattr(batch, f)[:sample].cpu() for f in ("src_des", "tgt_des", "src_xyz", "tgt_xyz", "T_gt", "perm", "inlier")])
+            v, dt, Tc, _ = cpu_baseline(c, sample, threads, hs)
+            same = bool(np.array_equal(Tc, T[:sample].cpu().numpy()))
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
+                                    "sample": "first %d pairs of the same workload, whole back end (oracle/bfr_oracle.c, OpenMP over pairs)" % sample,
+                                    "poses_bit_identical_to_gpu": same}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _measured_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    main()

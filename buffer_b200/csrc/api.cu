@@ -229,5 +229,18 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
     return BFR_OK;
 }
 
+int bfr_fp32_probe(int grid, int iters, float* scratch, void* stream)
+{
+    if (!scratch) return BFR_E_NULL;
+    if (grid <= 0 || iters < 0) return BFR_E_SIZE;
+    return cu(fp32_probe_launch(grid, iters, scratch, st(stream)));
+}
+
+int bfr_debug_set_k1_events(void* ev_start, void* ev_stop)
+{
+    k1_set_events(reinterpret_cast<cudaEvent_t>(ev_start), reinterpret_cast<cudaEvent_t>(ev_stop));
+    return BFR_OK;
+}
+
 #pragma GCC visibility pop
 }  // extern "C"

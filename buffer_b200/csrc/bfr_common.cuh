@@ -29,6 +29,7 @@ BFR_DEVINL float warp_max(float v) { float r; asm volatile("redux.sync.max.f32 %
 BFR_DEVINL uint32_t float_key(float v) { uint32_t b = __float_as_uint(v); return b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u); }
 BFR_DEVINL float key_float(uint32_t k) { uint32_t b = k ^ ((k & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu); return __uint_as_float(b); }
 BFR_DEVINL unsigned long long pack_best(uint32_t key, uint32_t idx) { return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - idx); }
+BFR_DEVINL void red_max_u64(unsigned long long* addr, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory"); }
 BFR_DEVINL uint32_t packed_index(unsigned long long p) { return 0xFFFFFFFFu - (uint32_t)(p & 0xFFFFFFFFull); }
 
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk) --------------------------------------------------------------

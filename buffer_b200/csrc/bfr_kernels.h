@@ -15,6 +15,9 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
                       cudaStream_t stream);
 cudaError_t gather_corr_launch(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr, cudaStream_t stream);
 
+cudaError_t fp32_probe_launch(int grid, int iters, float* scratch, cudaStream_t stream);
+void k1_set_events(cudaEvent_t e0, cudaEvent_t e1);
+
 // K2 + K3 (ransac.cu)
 cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
                           uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, int splits, unsigned long long* best_packed, cudaStream_t stream);

@@ -34,8 +34,8 @@ constexpr int K1_JC = 8;                      // columns per register chunk
 struct __align__(128) K1Smem {
     float b[K1_STAGES][K1_TILE][K1_D];        // 4 x 8 KB target tiles
     float hb[K1_STAGES][K1_TILE];             // -|b_j|^2/2 of the tile's columns
-    uint64_t full[K1_STAGES];
-    uint64_t empty[K1_STAGES];
+    uint64_t full[K1_STAGES];                 // TMA completion (expect_tx) barriers
+    int done[K1_STAGES];                      // warps that have finished reading the stage; the last one refills it
 };
 
 // ---- prep: half squared norms into the padded workspace (-inf in the padding) and zeroed packed bests ------------
@@ -65,6 +65,66 @@ __global__ void __launch_bounds__(256) k1_prep_kernel(const float* __restrict__ 
 }
 
 // ---- main kernel ----------------------------------------------------------------------------------------------
+// One 8-column chunk of the current tile against this thread's 4 stationary rows.  FULL = every column of the chunk is
+// a real target row (no bounds checks); the partial last tile of a pair uses FULL = false.
+template <bool FULL>
+BFR_DEVINL void k1_chunk(const K1Smem& sm, int stage, int j0, int ncols, int col0, const f32x2 (&ap)[2][K1_D], f32x2 hap0, f32x2 hap1,
+                         float (&rbest)[K1_RPT], int (&ridx)[K1_RPT], unsigned long long* __restrict__ colp, int i0)
+{
+    f32x2 acc[2][K1_JC];
+    {
+        const float4 h0 = *reinterpret_cast<const float4*>(&sm.hb[stage][j0]);
+        const float4 h1 = *reinterpret_cast<const float4*>(&sm.hb[stage][j0 + 4]);
+        const float hb[K1_JC] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w };
+#pragma unroll
+        for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = pack2(hb[jj], hb[jj]); acc[1][jj] = acc[0][jj]; }
+    }
+    // 16 independent accumulator pairs per k step: consecutive FFMA2 never depend on each other
+#pragma unroll
+    for (int k4 = 0; k4 < K1_D / 4; ++k4) {
+        float4 b[K1_JC];
+#pragma unroll
+        for (int jj = 0; jj < K1_JC; ++jj) b[jj] = *reinterpret_cast<const float4*>(&sm.b[stage][j0 + jj][4 * k4]);   // warp-uniform address
+#pragma unroll
+        for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = fma2(ap[0][4 * k4 + 0], pack2(b[jj].x, b[jj].x), acc[0][jj]); acc[1][jj] = fma2(ap[1][4 * k4 + 0], pack2(b[jj].x, b[jj].x), acc[1][jj]); }
+#pragma unroll
+        for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = fma2(ap[0][4 * k4 + 1], pack2(b[jj].y, b[jj].y), acc[0][jj]); acc[1][jj] = fma2(ap[1][4 * k4 + 1], pack2(b[jj].y, b[jj].y), acc[1][jj]); }
+#pragma unroll
+        for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = fma2(ap[0][4 * k4 + 2], pack2(b[jj].z, b[jj].z), acc[0][jj]); acc[1][jj] = fma2(ap[1][4 * k4 + 2], pack2(b[jj].z, b[jj].z), acc[1][jj]); }
+#pragma unroll
+        for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = fma2(ap[0][4 * k4 + 3], pack2(b[jj].w, b[jj].w), acc[0][jj]); acc[1][jj] = fma2(ap[1][4 * k4 + 3], pack2(b[jj].w, b[jj].w), acc[1][jj]); }
+    }
+    // ---- row direction: value-only chunk maximum, index recovered only on improvement -----------------------------
+    float v[K1_RPT][K1_JC];
+#pragma unroll
+    for (int jj = 0; jj < K1_JC; ++jj) { unpack2(acc[0][jj], v[0][jj], v[1][jj]); unpack2(acc[1][jj], v[2][jj], v[3][jj]); }
+#pragma unroll
+    for (int r = 0; r < K1_RPT; ++r) {
+        const float m = fmaxf(max3(v[r][0], v[r][1], v[r][2]), max3(v[r][3], v[r][4], max3(v[r][5], v[r][6], v[r][7])));
+        if (m > rbest[r]) {
+            int sel = K1_JC - 1;
+#pragma unroll
+            for (int jj = K1_JC - 2; jj >= 0; --jj) sel = (v[r][jj] == m) ? jj : sel;
+            rbest[r] = m; ridx[r] = col0 + j0 + sel;
+        }
+    }
+    // ---- column direction: add -|a_i|^2/2, one warp-wide max per column, the winning lane publishes ----------------
+#pragma unroll
+    for (int jj = 0; jj < K1_JC; ++jj) {
+        if (FULL || j0 + jj < ncols) {
+            float t0, t1, t2, t3;
+            unpack2(add2(acc[0][jj], hap0), t0, t1);
+            unpack2(add2(acc[1][jj], hap1), t2, t3);
+            const float m = fmaxf(max3(t0, t1, t2), t3);
+            const float wm = warp_max(m);
+            if (m == wm) {
+                const int r = (t0 == wm) ? 0 : (t1 == wm) ? 1 : (t2 == wm) ? 2 : 3;
+                red_max_u64(colp + col0 + j0 + jj, pack_best(float_key(wm), (uint32_t)(i0 + r)));
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(K1_THREADS, 2)
 k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
                     const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
@@ -91,7 +151,7 @@ k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt
     for (int i = threadIdx.x; i < K1_STAGES * K1_TILE * K1_D / 4; i += K1_THREADS)
         reinterpret_cast<float4*>(&sm.b[0][0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < K1_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], active_warps); }
+        for (int s = 0; s < K1_STAGES; ++s) { mbar_init(&sm.full[s], 1); sm.done[s] = 0; }
         mbar_fence_init();
     }
     fence_proxy_async();
@@ -126,90 +186,39 @@ k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt
         }
     }
     const float* hna_p = hna + (size_t)p * padM;
-    const float ha0 = hna_p[i0], ha1 = hna_p[i0 + 1], ha2 = hna_p[i0 + 2], ha3 = hna_p[i0 + 3];   // -inf beyond M
-    const f32x2 hap0 = pack2(ha0, ha1), hap1 = pack2(ha2, ha3);
+    const f32x2 hap0 = pack2(hna_p[i0], hna_p[i0 + 1]), hap1 = pack2(hna_p[i0 + 2], hna_p[i0 + 3]);   // -inf beyond M
 
     float rbest[K1_RPT]; int ridx[K1_RPT];
 #pragma unroll
     for (int r = 0; r < K1_RPT; ++r) { rbest[r] = -INFINITY; ridx[r] = 0; }
     unsigned long long* colp = col_packed + (size_t)p * padN;
 
+#pragma unroll 1
     for (int t = t_begin; t < t_end; ++t) {
         const int it = t - t_begin, stage = it % K1_STAGES;
-        const uint32_t phase = (uint32_t)(it / K1_STAGES) & 1u;
-        // producer: refill the stage the previous tile used (all warps have normally left it by now)
-        if (threadIdx.x == 0 && it >= 1 && t - 1 + K1_STAGES < t_end) {
-            const int ps = (it - 1) % K1_STAGES;
-            mbar_wait(&sm.empty[ps], (uint32_t)((it - 1) / K1_STAGES) & 1u);
-            issue_tile(t - 1 + K1_STAGES, ps);
-        }
-        __syncwarp();
-        mbar_wait(&sm.full[stage], phase);
-        const int ncols = min(K1_TILE, N - t * K1_TILE);
-        const int col0 = t * K1_TILE;
-
+        mbar_wait(&sm.full[stage], (uint32_t)(it / K1_STAGES) & 1u);
+        const int ncols = min(K1_TILE, N - t * K1_TILE), col0 = t * K1_TILE;
+        if (ncols == K1_TILE) {
 #pragma unroll 1
-        for (int j0 = 0; j0 < ncols; j0 += K1_JC) {
-            f32x2 acc[2][K1_JC];
-            {
-                const float4 h0 = *reinterpret_cast<const float4*>(&sm.hb[stage][j0]);
-                const float4 h1 = *reinterpret_cast<const float4*>(&sm.hb[stage][j0 + 4]);
-                const float hb[K1_JC] = { h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w };
-#pragma unroll
-                for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = pack2(hb[jj], hb[jj]); acc[1][jj] = acc[0][jj]; }
-            }
-#pragma unroll
-            for (int k4 = 0; k4 < K1_D / 4; ++k4) {
-#pragma unroll
-                for (int jj = 0; jj < K1_JC; ++jj) {
-                    const float4 b = *reinterpret_cast<const float4*>(&sm.b[stage][j0 + jj][4 * k4]);   // warp-uniform address
-                    acc[0][jj] = fma2(ap[0][4 * k4 + 0], pack2(b.x, b.x), acc[0][jj]);
-                    acc[1][jj] = fma2(ap[1][4 * k4 + 0], pack2(b.x, b.x), acc[1][jj]);
-                    acc[0][jj] = fma2(ap[0][4 * k4 + 1], pack2(b.y, b.y), acc[0][jj]);
-                    acc[1][jj] = fma2(ap[1][4 * k4 + 1], pack2(b.y, b.y), acc[1][jj]);
-                    acc[0][jj] = fma2(ap[0][4 * k4 + 2], pack2(b.z, b.z), acc[0][jj]);
-                    acc[1][jj] = fma2(ap[1][4 * k4 + 2], pack2(b.z, b.z), acc[1][jj]);
-                    acc[0][jj] = fma2(ap[0][4 * k4 + 3], pack2(b.w, b.w), acc[0][jj]);
-                    acc[1][jj] = fma2(ap[1][4 * k4 + 3], pack2(b.w, b.w), acc[1][jj]);
-                }
-            }
-            // ---- row direction: value-only chunk maximum, index recovered only on improvement ---------------------
-            float v[K1_RPT][K1_JC];
-#pragma unroll
-            for (int jj = 0; jj < K1_JC; ++jj) { unpack2(acc[0][jj], v[0][jj], v[1][jj]); unpack2(acc[1][jj], v[2][jj], v[3][jj]); }
-#pragma unroll
-            for (int r = 0; r < K1_RPT; ++r) {
-                const float m = fmaxf(max3(v[r][0], v[r][1], v[r][2]), max3(v[r][3], v[r][4], max3(v[r][5], v[r][6], v[r][7])));
-                if (m > rbest[r]) {
-                    int sel = K1_JC - 1;
-#pragma unroll
-                    for (int jj = K1_JC - 2; jj >= 0; --jj) sel = (v[r][jj] == m) ? jj : sel;
-                    rbest[r] = m; ridx[r] = col0 + j0 + sel;
-                }
-            }
-            // ---- column direction: add -|a_i|^2/2, one warp-wide max per column, winner publishes ------------------
-#pragma unroll
-            for (int jj = 0; jj < K1_JC; ++jj) {
-                if (j0 + jj < ncols) {
-                    float t0, t1, t2, t3;
-                    unpack2(add2(acc[0][jj], hap0), t0, t1);
-                    unpack2(add2(acc[1][jj], hap1), t2, t3);
-                    const float m = fmaxf(max3(t0, t1, t2), t3);
-                    const float wm = warp_max(m);
-                    if (m == wm) {
-                        const int r = (t0 == wm) ? 0 : (t1 == wm) ? 1 : (t2 == wm) ? 2 : 3;
-                        atomicMax(colp + col0 + j0 + jj, pack_best(float_key(wm), (uint32_t)(i0 + r)));
-                    }
-                }
+            for (int j0 = 0; j0 < K1_TILE; j0 += K1_JC) k1_chunk<true>(sm, stage, j0, ncols, col0, ap, hap0, hap1, rbest, ridx, colp, i0);
+        } else {
+#pragma unroll 1
+            for (int j0 = 0; j0 < ncols; j0 += K1_JC) k1_chunk<false>(sm, stage, j0, ncols, col0, ap, hap0, hap1, rbest, ridx, colp, i0);
+        }
+        // release the stage; the last warp out re-arms it with tile t + STAGES (no warp ever waits for a free slot)
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            if (atomicAdd(&sm.done[stage], 1) == active_warps - 1) {
+                sm.done[stage] = 0;
+                if (t + K1_STAGES < t_end) { fence_proxy_async(); issue_tile(t + K1_STAGES, stage); }
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);
     }
     unsigned long long* rowp = row_packed + (size_t)p * padM;
 #pragma unroll
     for (int r = 0; r < K1_RPT; ++r)
-        if (i0 + r < M) atomicMax(rowp + i0 + r, pack_best(float_key(rbest[r]), (uint32_t)ridx[r]));
+        if (i0 + r < M) red_max_u64(rowp + i0 + r, pack_best(float_key(rbest[r]), (uint32_t)ridx[r]));
 }
 
 // ---- select: decode packed bests, mutual check, ascending compaction, optional gather of matched keypoints --------
@@ -279,6 +288,38 @@ __global__ void gather_corr_kernel(const float* __restrict__ src_xyz, const floa
     corr[2 * (size_t)c + 1] = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.0f);
 }
 
+// ---- measurement aids ------------------------------------------------------------------------------------------
+// Pure FFMA2 stream (16 independent packed accumulators per thread): the FP32 issue peak the K1 roofline is
+// normalised against, measured live by bench.py on the GPU it runs on (MEASURED_PEAKS.json has no FP32 figure).
+__global__ void __launch_bounds__(256) fp32_probe_kernel(float* __restrict__ out, const float* __restrict__ in, int iters)
+{
+    f32x2 acc[16], a[4]; float b[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = pack2(in[(threadIdx.x + i) & 63], in[(threadIdx.x + i + 7) & 63]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { a[i] = pack2(in[64 + i + (threadIdx.x & 1)], in[68 + i + (threadIdx.x & 1)]); b[i] = in[72 + i + (threadIdx.x & 1)]; }
+    for (int it = 0; it < iters; ++it)
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = fma2(a[(i + u) & 3], pack2(b[u], b[u]), acc[i]);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { float x, y; unpack2(acc[i], x, y); s += x + y; }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// flops executed by one probe launch = grid * 256 threads * iters * 64 FFMA2 * 4
+cudaError_t fp32_probe_launch(int grid, int iters, float* scratch, cudaStream_t stream)
+{
+    // scratch: >= grid*256 + 128 floats; the first 128 are the (arbitrary, finite) inputs
+    fp32_probe_kernel<<<grid, 256, 0, stream>>>(scratch + 128, scratch, iters);
+    return cudaGetLastError();
+}
+
+static thread_local cudaEvent_t g_k1_ev0 = nullptr, g_k1_ev1 = nullptr;
+void k1_set_events(cudaEvent_t e0, cudaEvent_t e1) { g_k1_ev0 = e0; g_k1_ev1 = e1; }
+
 // ---- host launchers -------------------------------------------------------------------------------------------
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
@@ -318,8 +359,10 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     }
     if (col_splits < 1) col_splits = 1;
     dim3 grid((unsigned)((max_M + K1_ROWS - 1) / K1_ROWS), (unsigned)col_splits, (unsigned)P);
+    if (g_k1_ev0) cudaEventRecord(g_k1_ev0, stream);
     if (max_M > 0 && max_N > 0)
         k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);
+    if (g_k1_ev1) cudaEventRecord(g_k1_ev1, stream);
     k1_select_kernel<<<P, 256, 0, stream>>>(src_off, tgt_off, row_packed, col_packed, hna, padM, padN, nn_s, nn_t, d_s, d_t,
                                             src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, reinterpret_cast<float4*>(corr));
     return cudaGetLastError();

@@ -114,6 +114,15 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
                               float dist_th, float similar_th, float refine_thr, int refine_iters, int ransac_splits,
                               float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- measurement aids (used by bench.py only) ---------------------------------------------------------------------
+ * bfr_fp32_probe: a pure FFMA2 stream on `grid` CTAs of 256 threads, executing grid*256*iters*256 FMAs (2 flop each);
+ * scratch: device floats, >= grid*256 + 128, first 128 initialised by the caller to finite values.  The measured rate
+ * is the FP32 issue peak the mutual-NN roofline is normalised against.
+ * bfr_debug_set_k1_events: cudaEvent_t pair (or NULLs to disable) recorded immediately before / after the main
+ * mutual-NN kernel by subsequent calls made from THIS host thread; lets bench.py time that kernel inside the full step. */
+int bfr_fp32_probe(int grid, int iters, float* scratch, void* stream);
+int bfr_debug_set_k1_events(void* ev_start, void* ev_stop);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,11 @@ BFR_DEVINL uint32_t float_key(float v) { uint32_t b = __float_as_uint(v); return
 BFR_DEVINL float key_float(uint32_t k) { uint32_t b = k ^ ((k & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu); return __uint_as_float(b); }
 BFR_DEVINL unsigned long long pack_best(uint32_t key, uint32_t idx) { return ((unsigned long long)key << 32) | (unsigned long long)(0xFFFFFFFFu - idx); }
 BFR_DEVINL void red_max_u64(unsigned long long* addr, unsigned long long v) { asm volatile("red.global.max.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory"); }
+// predicated form: publishes only in lanes where a == b (no branch, so independent reductions can interleave)
+BFR_DEVINL void red_max_u64_if_eq(unsigned long long* addr, unsigned long long v, float a, float b)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.eq.f32 q, %2, %3;\n\t@q red.global.max.u64 [%0], %1;\n\t}" ::"l"(addr), "l"(v), "f"(a), "f"(b) : "memory");
+}
 BFR_DEVINL uint32_t packed_index(unsigned long long p) { return 0xFFFFFFFFu - (uint32_t)(p & 0xFFFFFFFFull); }
 
 // ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk) --------------------------------------------------------------

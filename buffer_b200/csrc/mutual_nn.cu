@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(256) k1_prep_kernel(const float* __restrict__ 
 // a real target row (no bounds checks); the partial last tile of a pair uses FULL = false.
 template <bool FULL>
 BFR_DEVINL void k1_chunk(const K1Smem& sm, int stage, int j0, int ncols, int col0, const f32x2 (&ap)[2][K1_D], f32x2 hap0, f32x2 hap1,
-                         float (&rbest)[K1_RPT], int (&ridx)[K1_RPT], unsigned long long* __restrict__ colp, int i0)
+                         float (&rbest)[K1_RPT], int (&ridx)[K1_RPT], unsigned long long* __restrict__ colp, const uint32_t (&nrow)[K1_RPT])
 {
     f32x2 acc[2][K1_JC];
     {
@@ -94,33 +94,44 @@ BFR_DEVINL void k1_chunk(const K1Smem& sm, int stage, int j0, int ncols, int col
 #pragma unroll
         for (int jj = 0; jj < K1_JC; ++jj) { acc[0][jj] = fma2(ap[0][4 * k4 + 3], pack2(b[jj].w, b[jj].w), acc[0][jj]); acc[1][jj] = fma2(ap[1][4 * k4 + 3], pack2(b[jj].w, b[jj].w), acc[1][jj]); }
     }
-    // ---- row direction: value-only chunk maximum, index recovered only on improvement -----------------------------
-    float v[K1_RPT][K1_JC];
+    // ---- row direction: value-only chunk maxima; one rarely-taken branch recovers indices for the rows that improved --
+    float v[K1_RPT][K1_JC], cm[K1_RPT];
 #pragma unroll
     for (int jj = 0; jj < K1_JC; ++jj) { unpack2(acc[0][jj], v[0][jj], v[1][jj]); unpack2(acc[1][jj], v[2][jj], v[3][jj]); }
 #pragma unroll
-    for (int r = 0; r < K1_RPT; ++r) {
-        const float m = fmaxf(max3(v[r][0], v[r][1], v[r][2]), max3(v[r][3], v[r][4], max3(v[r][5], v[r][6], v[r][7])));
-        if (m > rbest[r]) {
-            int sel = K1_JC - 1;
+    for (int r = 0; r < K1_RPT; ++r)
+        cm[r] = fmaxf(max3(v[r][0], v[r][1], v[r][2]), max3(v[r][3], v[r][4], max3(v[r][5], v[r][6], v[r][7])));
+    if ((cm[0] > rbest[0]) | (cm[1] > rbest[1]) | (cm[2] > rbest[2]) | (cm[3] > rbest[3])) {
 #pragma unroll
-            for (int jj = K1_JC - 2; jj >= 0; --jj) sel = (v[r][jj] == m) ? jj : sel;
-            rbest[r] = m; ridx[r] = col0 + j0 + sel;
+        for (int r = 0; r < K1_RPT; ++r) {
+            if (cm[r] > rbest[r]) {
+                int sel = K1_JC - 1;
+#pragma unroll
+                for (int jj = K1_JC - 2; jj >= 0; --jj) sel = (v[r][jj] == cm[r]) ? jj : sel;
+                rbest[r] = cm[r]; ridx[r] = col0 + j0 + sel;
+            }
         }
     }
-    // ---- column direction: add -|a_i|^2/2, one warp-wide max per column, the winning lane publishes ----------------
+    // ---- column direction: add -|a_i|^2/2, one warp-wide max per column (8 independent CREDUX chains), the lanes that
+    //      hold the maximum publish (value key << 32 | ~row) with a predicated 64-bit RED.MAX -------------------------------
+    float m[K1_JC], wm[K1_JC];
+#pragma unroll
+    for (int jj = 0; jj < K1_JC; ++jj) {
+        acc[0][jj] = add2(acc[0][jj], hap0);
+        acc[1][jj] = add2(acc[1][jj], hap1);
+        unpack2(acc[0][jj], v[0][jj], v[1][jj]); unpack2(acc[1][jj], v[2][jj], v[3][jj]);
+        m[jj] = fmaxf(max3(v[0][jj], v[1][jj], v[2][jj]), v[3][jj]);
+    }
+#pragma unroll
+    for (int jj = 0; jj < K1_JC; ++jj) wm[jj] = warp_max(m[jj]);
 #pragma unroll
     for (int jj = 0; jj < K1_JC; ++jj) {
         if (FULL || j0 + jj < ncols) {
-            float t0, t1, t2, t3;
-            unpack2(add2(acc[0][jj], hap0), t0, t1);
-            unpack2(add2(acc[1][jj], hap1), t2, t3);
-            const float m = fmaxf(max3(t0, t1, t2), t3);
-            const float wm = warp_max(m);
-            if (m == wm) {
-                const int r = (t0 == wm) ? 0 : (t1 == wm) ? 1 : (t2 == wm) ? 2 : 3;
-                red_max_u64(colp + col0 + j0 + jj, pack_best(float_key(wm), (uint32_t)(i0 + r)));
-            }
+            uint32_t lo = nrow[3];                                  // lowest row of this thread that attains the maximum
+            lo = (v[2][jj] == wm[jj]) ? nrow[2] : lo;
+            lo = (v[1][jj] == wm[jj]) ? nrow[1] : lo;
+            lo = (v[0][jj] == wm[jj]) ? nrow[0] : lo;
+            red_max_u64_if_eq(colp + col0 + j0 + jj, ((unsigned long long)float_key(wm[jj]) << 32) | lo, m[jj], wm[jj]);
         }
     }
 }
@@ -188,9 +199,9 @@ k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt
     const float* hna_p = hna + (size_t)p * padM;
     const f32x2 hap0 = pack2(hna_p[i0], hna_p[i0 + 1]), hap1 = pack2(hna_p[i0 + 2], hna_p[i0 + 3]);   // -inf beyond M
 
-    float rbest[K1_RPT]; int ridx[K1_RPT];
+    float rbest[K1_RPT]; int ridx[K1_RPT]; uint32_t nrow[K1_RPT];           // nrow = low word of the packed best: ~row index
 #pragma unroll
-    for (int r = 0; r < K1_RPT; ++r) { rbest[r] = -INFINITY; ridx[r] = 0; }
+    for (int r = 0; r < K1_RPT; ++r) { rbest[r] = -INFINITY; ridx[r] = 0; nrow[r] = 0xFFFFFFFFu - (uint32_t)(i0 + r); }
     unsigned long long* colp = col_packed + (size_t)p * padN;
 
 #pragma unroll 1
@@ -200,10 +211,10 @@ k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt
         const int ncols = min(K1_TILE, N - t * K1_TILE), col0 = t * K1_TILE;
         if (ncols == K1_TILE) {
 #pragma unroll 1
-            for (int j0 = 0; j0 < K1_TILE; j0 += K1_JC) k1_chunk<true>(sm, stage, j0, ncols, col0, ap, hap0, hap1, rbest, ridx, colp, i0);
+            for (int j0 = 0; j0 < K1_TILE; j0 += K1_JC) k1_chunk<true>(sm, stage, j0, ncols, col0, ap, hap0, hap1, rbest, ridx, colp, nrow);
         } else {
 #pragma unroll 1
-            for (int j0 = 0; j0 < ncols; j0 += K1_JC) k1_chunk<false>(sm, stage, j0, ncols, col0, ap, hap0, hap1, rbest, ridx, colp, i0);
+            for (int j0 = 0; j0 < ncols; j0 += K1_JC) k1_chunk<false>(sm, stage, j0, ncols, col0, ap, hap0, hap1, rbest, ridx, colp, nrow);
         }
         // release the stage; the last warp out re-arms it with tile t + STAGES (no warp ever waits for a free slot)
         __syncwarp();

@@ -1,0 +1,142 @@
+"""CPU tests (no GPU): the oracle (oracle/bfr_oracle.c) against the golden fixtures generated from the UNMODIFIED reference
+(tests/golden/*.npz, oracle/gen_golden.py) and against the Philox known-answer vectors.  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from buffer_b200 import synthetic as S
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(G, name + ".npz"))
+
+
+def rot_err(Ra, Rb):
+    return float(S.rotation_error_rad(torch.from_numpy(np.asarray(Ra, np.float64)), torch.from_numpy(np.asarray(Rb, np.float64))))
+
+
+def test_philox4x32_10_known_answers(oracle):
+    # Random123 kat_vectors: philox4x32 10 rounds
+    kats = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+            ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+            ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0], [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, out in kats:
+        assert [int(x) for x in oracle.philox4x32_10(ctr, key)] == out
+
+
+def test_sample3_is_mulhi_of_philox(oracle):
+    for h, K in ((0, 5000), (123456, 1501), (49999, 3)):
+        r = oracle.philox4x32_10([h, 77, 0, 0], [0xDEADBEEF, 0x12345678])
+        want = [(int(x) * K) >> 32 for x in r[:3]]
+        assert [int(x) for x in oracle.sample3(0x12345678DEADBEEF, 77, h, K)] == want
+
+
+def test_mutual_matching_equals_reference(oracle):
+    g = load("mutual_matching")
+    s, t = oracle.mutual_matching(g["src_des"], g["tgt_des"])
+    assert s.dtype == np.int64 and np.array_equal(s, g["s_mids"]) and np.array_equal(t, g["t_mids"])
+    assert np.all(np.diff(s) > 0)
+
+
+@pytest.mark.parametrize("case", ["n3", "n3_noise", "n200_w", "n200_wthr", "n2000", "mirror"])
+def test_rigid_transform_3d_equals_reference(oracle, case):
+    g = load("rigid_transform_3d")
+    w = g[case + "_w"].copy() if case + "_w" in g.files else None
+    T = oracle.rigid_transform_3d(g[case + "_A"], g[case + "_B"], w, float(g[case + "_thr"]))
+    Tr = g[case + "_T"]
+    assert T.shape == Tr.shape
+    for b in range(T.shape[0]):
+        assert rot_err(T[b, :3, :3], Tr[b, :3, :3]) < 1e-5            # north_star tolerance: 1e-5 rad
+        assert np.abs(T[b, :3, 3] - Tr[b, :3, 3]).max() < 1e-5        # 1e-5 m
+        assert abs(np.linalg.det(T[b, :3, :3].astype(np.float64)) - 1) < 1e-5
+    assert np.array_equal(T[:, 3], np.tile(np.array([0, 0, 0, 1], np.float32), (T.shape[0], 1)))
+
+
+def test_post_refinement_equals_reference(oracle):
+    g = load("post_refinement")
+    corr = np.zeros((len(g["src"]), 8), np.float32); corr[:, :3] = g["src"]; corr[:, 4:7] = g["tgt"]
+    for key, thr in (("T_3dmatch", 0.10), ("T_kitti", 1.2)):
+        T, it, inl = oracle.post_refinement(g["T0"], corr, thr, 20)
+        assert rot_err(T[:3, :3], g[key][:3, :3]) < 1e-5 and np.abs(T[:3, 3] - g[key][:3, 3]).max() < 1e-5
+        assert 1 <= it <= 20 and inl > 0
+    T, it, inl = oracle.post_refinement(g["T0_far"], corr, 0.10, 20)
+    assert np.array_equal(T, g["T_far"]) and it == 0 and inl == 0     # no inliers: returned unchanged (models/BUFFER.py:406-407)
+
+
+def test_lrf_hypotheses_and_scoring_equal_reference(oracle):
+    g = load("lrf_scoring")
+    ang = g["ind"].astype(np.float64) * 2 * np.pi / 20 + 1e-6
+    cs = np.stack([np.cos(ang), np.sin(ang)], -1).astype(np.float32)
+    R, t = oracle.lrf_hypotheses(cs, g["ss_R"], g["tt_R"], g["ss"], g["tt"])
+    assert np.abs(R - g["R"]).max() < 5e-6 and np.abs(t - g["t"]).max() < 2e-5
+    # scoring of the REFERENCE's hypotheses so that only the scoring arithmetic is compared
+    counts, best, mask = oracle.score_hypotheses(g["R"], g["t"], g["ss"], g["tt"], g["thr"])
+    assert best == int(g["best_ind"])
+    assert np.array_equal(np.nonzero(mask)[0], g["inlier_ind"])
+    diff = counts.astype(np.int64) - g["inlier_num"]
+    assert np.abs(diff).max() <= 1 and np.mean(diff != 0) < 0.01      # d2 < thr^2 vs sqrt(d2) < thr: borderline cases only
+    assert counts.max() == g["inlier_num"].max()
+
+
+def test_ransac_equals_reference_semantics(oracle):
+    g = load("ransac")
+    K = len(g["ss"]); H = int(g["H"]); seed = int(g["seed"]); pid = int(g["pair_id"])
+    corr = np.zeros((K, 8), np.float32); corr[:, :3] = g["ss"]; corr[:, 4:7] = g["tt"]
+    for h in range(0, H, 37):                                          # shared Philox stream -> identical minimal sets
+        assert [int(x) for x in oracle.sample3(seed, pid, h, K)] == [int(x) for x in g["samples"][h]]
+    best, counts = oracle.ransac(corr, seed, pid, H, float(g["dist_th"]), float(g["similar_th"]), want_counts=True)
+    ref = g["counts"]
+    valid_o, valid_r = counts >= 0, ref >= 0
+    assert np.mean(valid_o != valid_r) < 0.01                          # checker decisions agree (borderline fits may flip)
+    both = valid_o & valid_r
+    assert both.sum() > 5 and np.abs(counts[both] - ref[both]).max() <= 1
+    T, cnt, bh = oracle.ransac_finalize(corr, seed, pid, best, float(g["dist_th"]), float(g["similar_th"]))
+    assert bh == int(g["best_h"]) and abs(cnt - int(g["best_count"])) <= 1
+    assert rot_err(T[:3, :3], g["T_best"][:3, :3]) < 1e-5 and np.abs(T[:3, 3] - g["T_best"][:3, 3]).max() < 1e-5
+    ok, rte, rre = S.registration_recall(torch.from_numpy(T)[None], torch.from_numpy(g["T_gt"])[None])
+    assert ok == 1.0
+
+
+def test_oracle_properties(oracle):
+    """SE(3) recovery from noiseless inliers, invariance to outlier positions, SO(3) membership, K < 3 -> identity"""
+    b = S.make_pairs(2, 600, cfg_id=55, sigma=0.0)
+    for p in range(2):
+        s, t = oracle.mutual_matching(b.src_des[p].numpy(), b.tgt_des[p].numpy())
+        assert np.array_equal(t, b.perm[p].numpy()[s]) and len(s) == 600
+        corr = oracle.gather_corr(b.src_xyz[p].numpy(), b.tgt_xyz[p].numpy(), s, t)
+        best = oracle.ransac(corr, 11, p, 3000, 0.1, 0.8)
+        T, cnt, bh = oracle.ransac_finalize(corr, 11, p, best, 0.1, 0.8)
+        assert cnt == int(b.inlier[p].sum()) and bh >= 0
+        assert rot_err(T[:3, :3], b.T_gt[p, :3, :3].numpy()) < 1e-5 and np.abs(T[:3, 3] - b.T_gt[p, :3, 3].numpy()).max() < 1e-5
+        R = T[:3, :3].astype(np.float64)
+        assert np.abs(R @ R.T - np.eye(3)).max() < 1e-6 and abs(np.linalg.det(R) - 1) < 1e-6
+        # move the outliers somewhere else: same winner, same pose
+        corr2 = corr.copy(); out = ~b.inlier[p].numpy()[s]; corr2[out, 4:7] += 7.0
+        best2 = oracle.ransac(corr2, 11, p, 3000, 0.1, 0.8)
+        assert best2 == best
+    for K in (0, 1, 2):
+        c = np.random.RandomState(K).randn(max(K, 1), 8).astype(np.float32)[:K]
+        assert oracle.ransac(c.reshape(K, 8), 1, 0, 100, 0.1, 0.8) == 0
+        T, cnt, bh = oracle.ransac_finalize(c.reshape(K, 8), 1, 0, 0, 0.1, 0.8)
+        assert np.array_equal(T, np.eye(4, dtype=np.float32)) and cnt == 0 and bh == -1
+
+
+def test_oracle_kabsch_reflection_and_degenerate(oracle):
+    rng = np.random.RandomState(3)
+    for _ in range(50):
+        A = rng.randn(30, 3); q = rng.randn(4); q /= np.linalg.norm(q)
+        Rg = S.quat_to_rot(torch.from_numpy(q)[None].float())[0].numpy().astype(np.float64)
+        Bm = A @ Rg.T; Bm[:, 0] *= -1                                   # improper: needs the reflection fix
+        H = ((A - A.mean(0)).T @ (Bm - Bm.mean(0))).astype(np.float32)
+        R, ok = oracle.kabsch_rotation(H)
+        U, Sv, Vt = np.linalg.svd(H.astype(np.float64)); V = Vt.T
+        Rr = V @ np.diag([1, 1, np.linalg.det(V @ U.T)]) @ U.T
+        assert ok and abs(np.linalg.det(R.astype(np.float64)) - 1) < 1e-5 and rot_err(R, Rr) < 1e-4
+    R, ok = oracle.kabsch_rotation(np.outer([1, 2, 3], [3, 2, 1]).astype(np.float32))   # rank 1: rejected
+    assert not ok and np.array_equal(R, np.eye(3, dtype=np.float32))
+    R, ok = oracle.kabsch_rotation(np.zeros((3, 3), np.float32))
+    assert not ok

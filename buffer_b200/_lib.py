@@ -14,8 +14,10 @@ _vp, _i, _u32, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64, C.c_
 SIGNATURES = {
     "bfr_version": (_i, []),
     "bfr_error_string": (C.c_char_p, [_i]),
+    "bfr_config_set": (_i, [_i, _i]),
+    "bfr_config_get": (_i, [_i]),
     "bfr_mutual_nn_workspace_bytes": (_sz, [_i, _i, _i]),
-    "bfr_mutual_matching_batched": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bfr_mutual_matching_batched": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_gather_corr": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "bfr_ransac_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _u32, _u32, _f, _f, _i, _vp, _vp]),
     "bfr_ransac_finalize_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _f, _f, _vp, _vp, _vp, _vp, _vp]),

@@ -23,6 +23,17 @@ from . import _lib
 
 DESC_DIM = 32
 _workspaces = {}
+K1_FP32, K1_TENSOR_FILTER = 0, 1
+
+
+def set_k1_algo(algo):
+    """select the mutual-NN kernel: K1_FP32 (all products in FP32) or K1_TENSOR_FILTER (tcgen05 TF32 filter + exact FP32
+    re-check); outputs are bit-identical"""
+    _lib.check(_lib.lib().bfr_config_set(1, int(algo)), "bfr_config_set")
+
+
+def get_k1_algo():
+    return _lib.lib().bfr_config_get(1)
 
 
 def _stream():
@@ -96,7 +107,7 @@ def mutual_matching_batched(src_des, tgt_des, src_off, tgt_off, max_M, max_N, sr
     nbytes = L.bfr_mutual_nn_workspace_bytes(P, max_M, max_N)
     ws = _ws(nbytes, dev, "k1")
     _lib.check(L.bfr_mutual_matching_batched(src_des.data_ptr(), tgt_des.data_ptr(), src_off.data_ptr(), tgt_off.data_ptr(),
-                                             P, max_M, max_N, DESC_DIM, col_splits,
+                                             P, max_M, max_N, totM, totN, DESC_DIM, col_splits,
                                              _ptr(out["nn_s"]), _ptr(out["nn_t"]), _ptr(out["dist_s"]), _ptr(out["dist_t"]),
                                              _ptr(src_xyz), _ptr(tgt_xyz), _ptr(out["s_mids"]), _ptr(out["t_mids"]),
                                              out["n_mutual"].data_ptr(), _ptr(corr), ws.data_ptr(), ws.numel(), _stream()),

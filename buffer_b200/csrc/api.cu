@@ -59,20 +59,20 @@ const char* bfr_error_string(int code)
 size_t bfr_mutual_nn_workspace_bytes(int P, int max_M, int max_N) { return k1_workspace_bytes(P < 0 ? 0 : P, max_M, max_N); }
 
 int bfr_mutual_matching_batched(const float* src_des, const float* tgt_des, const int32_t* src_off, const int32_t* tgt_off,
-                                int P, int max_M, int max_N, int D, int col_splits,
+                                int P, int max_M, int max_N, int total_M, int total_N, int D, int col_splits,
                                 int64_t* nn_s, int64_t* nn_t, float* dist_s, float* dist_t,
                                 const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr_xyz,
                                 void* ws, size_t ws_bytes, void* stream)
 {
     if (P == 0) return BFR_OK;
     if (!src_des || !tgt_des || !src_off || !tgt_off || !ws) return BFR_E_NULL;
-    if (P < 0 || max_M < 0 || max_N < 0) return BFR_E_SIZE;
+    if (P < 0 || max_M < 0 || max_N < 0 || total_M < 0 || total_N < 0) return BFR_E_SIZE;
     if (D != 32) return BFR_E_DIM;
     if (!aligned16(src_des) || !aligned16(tgt_des)) return BFR_E_ALIGN;
     if (ws_bytes < k1_workspace_bytes(P, max_M, max_N)) return BFR_E_WORKSPACE;
     if (corr_xyz && (!src_xyz || !tgt_xyz)) return BFR_E_NULL;
     if ((s_mids == nullptr) != (t_mids == nullptr)) return BFR_E_NULL;
-    return cu(k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, D, col_splits, ws, nn_s, nn_t, dist_s, dist_t,
+    return cu(k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, total_M, total_N, D, col_splits, ws, nn_s, nn_t, dist_s, dist_t,
                         src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, corr_xyz, st(stream)));
 }
 
@@ -171,7 +171,7 @@ int bfr_register_batched(const float* src_des, const float* src_xyz, const int32
     RegWs w = reg_ws_carve(ws, P, max_M, max_N, total_M);
     cudaError_t e = cudaMemsetAsync(w.best, 0, (size_t)P * 8, s);
     if (e != cudaSuccess) return (int)e;
-    e = k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, D, 1, w.k1, nullptr, nullptr, nullptr, nullptr,
+    e = k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, total_M, total_N, D, 1, w.k1, nullptr, nullptr, nullptr, nullptr,
                   src_xyz, tgt_xyz, nullptr, nullptr, n_mutual, w.corr, s);
     if (e != cudaSuccess) return (int)e;
     e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, ransac_splits, w.best, s);
@@ -227,6 +227,18 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
     if (n_mutual_host && (e = cudaMemcpyAsync(n_mutual_host, d_nm, (size_t)P * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
     if (n_inliers_host && (e = cudaMemcpyAsync(n_inliers_host, d_ni, (size_t)P * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
     return BFR_OK;
+}
+
+int bfr_config_set(int key, int value)
+{
+    if (key == BFR_CFG_K1_ALGO) { if (value != 0 && value != 1) return BFR_E_SIZE; k1_set_algo(value); return BFR_OK; }
+    return BFR_E_SIZE;
+}
+
+int bfr_config_get(int key)
+{
+    if (key == BFR_CFG_K1_ALGO) return k1_get_algo();
+    return BFR_E_SIZE;
 }
 
 int bfr_fp32_probe(int grid, int iters, float* scratch, void* stream)

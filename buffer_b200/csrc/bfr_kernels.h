@@ -9,8 +9,14 @@ namespace bfr {
 // K1 (mutual_nn.cu)
 int k1_pad_rows(int max_rows);
 size_t k1_workspace_bytes(int P, int max_M, int max_N);
-cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N, int D,
-                      int col_splits, void* ws, int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t,
+void k1_set_algo(int algo);
+int k1_get_algo();
+bool k1_tc_supported(int D, long long total_M, long long total_N);
+cudaError_t k1_tc_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+                         long long total_M, long long total_N, const float* hna, const float* hnb, int padM, int padN,
+                         unsigned long long* row_packed, unsigned long long* col_packed, cudaStream_t stream);
+cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+                      long long total_M, long long total_N, int D, int col_splits, void* ws, int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t,
                       const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr,
                       cudaStream_t stream);
 cudaError_t gather_corr_launch(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr, cudaStream_t stream);

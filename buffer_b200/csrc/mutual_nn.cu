@@ -342,8 +342,12 @@ size_t k1_workspace_bytes(int P, int max_M, int max_N)
     return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long)) + 256;
 }
 
-cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N, int D,
-                      int col_splits, void* ws, int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t,
+static int g_k1_algo = 0;                       // 0 = FP32 FFMA2 kernel, 1 = tensor-core filter + exact re-check (mutual_nn_tc.cu)
+void k1_set_algo(int algo) { g_k1_algo = algo; }
+int k1_get_algo() { return g_k1_algo; }
+
+cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+                      long long total_M, long long total_N, int D, int col_splits, void* ws, int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t,
                       const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr,
                       cudaStream_t stream)
 {
@@ -371,8 +375,14 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     if (col_splits < 1) col_splits = 1;
     dim3 grid((unsigned)((max_M + K1_ROWS - 1) / K1_ROWS), (unsigned)col_splits, (unsigned)P);
     if (g_k1_ev0) cudaEventRecord(g_k1_ev0, stream);
-    if (max_M > 0 && max_N > 0)
-        k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);
+    if (max_M > 0 && max_N > 0) {
+        if (g_k1_algo == 1 && k1_tc_supported(D, total_M, total_N)) {
+            cudaError_t e = k1_tc_launch(src, tgt, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
+            if (e != cudaSuccess) return e;
+        } else {
+            k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);
+        }
+    }
     if (g_k1_ev1) cudaEventRecord(g_k1_ev1, stream);
     k1_select_kernel<<<P, 256, 0, stream>>>(src_off, tgt_off, row_packed, col_packed, hna, padM, padN, nn_s, nn_t, d_s, d_t,
                                             src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, reinterpret_cast<float4*>(corr));

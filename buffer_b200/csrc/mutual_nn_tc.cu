@@ -1,0 +1,331 @@
+// mutual_nn_tc.cu — K1-TC: tensor-core *filter* + exact FP32 re-check for the mutual-NN argmax (sm_100a, tcgen05/TMEM/TMA).
+//
+// Same contract and bit-exact results as k1_mutual_nn_kernel (mutual_nn.cu / oracle orc_mutual_nn), ~10x less FP32 work:
+//   1. S~ = A B^T with tcgen05.mma kind::tf32 (M=128, N=128, K=8 per instruction, accumulators in TMEM).  TF32 keeps 11
+//      significand bits, so |S~_ij - a_i.b_j| <= 2^-9 |a_i||b_j|; with eps = 2^-8 |a_i| max_j|b_j| every column whose exact
+//      score could be the row maximum satisfies  S~_ij + hn(b_j) >= max_j(S~_ij + hn(b_j)) - 2 eps.
+//   2. The epilogue (one thread per row, TMEM -> registers with tcgen05.ld) keeps the running approximate maximum and a
+//      short list of 8-column groups whose maximum was inside the 2-eps band when they streamed past (compacted when full).
+//   3. Each thread re-evaluates its few candidates with the EXACT FP32 chain of the oracle (acc = hn(b); acc = fma(a_k, b_k,
+//      acc), k ascending) and publishes (key << 32 | ~index) with the same 64-bit RED.MAX as the FP32 kernel, so ties still
+//      go to the lowest index and the result is bit-identical by construction.  A list overflow (many near-duplicate
+//      descriptors) falls back to an exact scan of the row.
+// The column direction (tgt -> src) is the same kernel with the roles of the two descriptor sets swapped.
+//
+// Warp roles (320 threads, 1 CTA/SM, 256 own rows, 512 TMEM columns = 2 buffers x 2 row halves x 128 columns):
+//   warp 0   TMA producer: the CTA's 256 "own" rows once, then 128-row tiles of the streamed side through a 4-stage ring
+//            (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier expect-tx)
+//   warp 1   TMEM allocator + MMA issuer: 2 halves x 4 tcgen05.mma (K = 4 x 8) per tile, tcgen05.commit -> ring slot free / accumulator full
+//   warps 2-9 epilogue (one thread per own row): tcgen05.ld 32 columns at a time, add hn(b_j) (shared-memory broadcast),
+//            FMNMX3 tree per 8-column group, predicated append of the groups inside the band
+#include "bfr_common.cuh"
+#include "bfr_kernels.h"
+#include <cuda.h>
+#include <cmath>
+
+namespace bfr {
+
+constexpr int TC_BM = 256;                      // own rows per CTA = two M=128 accumulator halves sharing every streamed tile
+constexpr int TC_BN = 128;                      // streamed rows per tile (MMA N)
+constexpr int TC_D = 32;
+constexpr int TC_STAGES = 4;
+constexpr int TC_EPI_WARPS = 8;                 // one epilogue thread per own row
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_SUB = 8;                       // candidate granularity: 8-column groups
+constexpr int TC_CAP = 24;                      // candidate groups kept per row
+constexpr int TC_MAX_TILES = 64;                // streamed tiles per CTA (hn cache = 8192 floats)
+
+struct TcSmem {
+    float a[TC_BM * TC_D];                      // 32 KB, SWIZZLE_128B K-major (one 128-byte atom per row); rows 128.. = second half
+    float b[TC_STAGES][TC_BN * TC_D];           // 4 x 16 KB
+    float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
+    float cv[TC_CAP][TC_BM];                    // candidate group maxima (approximate scores)  [slot][row]
+    int ci[TC_CAP][TC_BM];                      // first streamed column of the candidate group
+    float red[TC_THREADS / 32];
+    uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+};
+
+BFR_DEVINL void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+BFR_DEVINL uint64_t umma_desc_sw128(const void* smem)
+{   // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell)
+    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+BFR_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+BFR_DEVINL void umma_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
+BFR_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+BFR_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+BFR_DEVINL void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+                   "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                   "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// exact score of (own row, candidate row) — the oracle's chain.  COLDIR = the "own" side is the target set.
+template <bool COLDIR>
+BFR_DEVINL float exact_score(const float4 (&own)[8], float own_hn, const float* __restrict__ cand_row, float cand_hn)
+{
+    float acc = COLDIR ? own_hn : cand_hn;
+    const float4* c4 = reinterpret_cast<const float4*>(cand_row);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 c = __ldg(c4 + k4);
+        acc = __fmaf_rn(own[k4].x, c.x, acc); acc = __fmaf_rn(own[k4].y, c.y, acc);
+        acc = __fmaf_rn(own[k4].z, c.z, acc); acc = __fmaf_rn(own[k4].w, c.w, acc);
+    }
+    return COLDIR ? __fadd_rn(acc, cand_hn) : acc;
+}
+
+template <bool COLDIR>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant__ CUtensorMap map_str,
+             const float* __restrict__ x_own, const float* __restrict__ x_str,
+             const int32_t* __restrict__ off_own, const int32_t* __restrict__ off_str,
+             const float* __restrict__ hn_own, const float* __restrict__ hn_str, int pad_own, int pad_str,
+             unsigned long long* __restrict__ out_packed, int splits)
+{
+    extern __shared__ unsigned char smem_raw[];
+    TcSmem& sm = *reinterpret_cast<TcSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+
+    const int p = blockIdx.z;
+    const int oo = off_own[p], M = off_own[p + 1] - oo;
+    const int os = off_str[p], N = off_str[p + 1] - os;
+    const int row0 = blockIdx.x * TC_BM;
+    if (row0 >= M || N <= 0) return;
+    const int ntiles_all = (N + TC_BN - 1) / TC_BN;
+    const int t_begin = (int)(((long long)blockIdx.y * ntiles_all) / splits);
+    const int t_end = (int)(((long long)(blockIdx.y + 1) * ntiles_all) / splits);
+    const int ntiles = t_end - t_begin;
+    if (ntiles <= 0) return;
+    const int halves = (M - row0 > 128) ? 2 : 1;                      // second accumulator half only if it has rows
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* hn_str_p = hn_str + (size_t)p * pad_str;
+
+    // ---- setup: barriers, TMEM, streamed half-norms (+ their minimum = largest streamed norm) ----------------------
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.a_full, 1);
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&sm.acc_full[a], 1); mbar_init(&sm.acc_empty[a], 4 * halves); }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    float hmin = 0.0f;
+    for (int i = threadIdx.x; i < ntiles * TC_BN; i += TC_THREADS) {
+        const float h = hn_str_p[t_begin * TC_BN + i];               // padded array: -inf beyond N
+        sm.hn[i] = h;
+        if (h > -INFINITY) hmin = fminf(hmin, h);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) hmin = fminf(hmin, __shfl_xor_sync(0xffffffffu, hmin, o));
+    if (lane == 0) sm.red[warp] = hmin;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+#pragma unroll
+    for (int w = 0; w < TC_THREADS / 32; ++w) hmin = fminf(hmin, sm.red[w]);
+    const float str_max_sq = -2.0f * hmin;                            // max_j |b_j|^2 over this CTA's columns
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(&sm.a_full, TC_BM * TC_D * 4);
+            tma_load_2d(sm.a, &map_own, 0, oo + row0, &sm.a_full);
+            for (int it = 0; it < ntiles; ++it) {
+                const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                mbar_wait(&sm.empty[s], ph ^ 1u);
+                mbar_expect_tx(&sm.full[s], TC_BN * TC_D * 4);
+                tma_load_2d(sm.b[s], &map_str, 0, os + (t_begin + it) * TC_BN, &sm.full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t adesc0 = umma_desc_sw128(sm.a), adesc1 = umma_desc_sw128(sm.a + 128 * TC_D);
+            mbar_wait(&sm.a_full, 0);
+            for (int it = 0; it < ntiles; ++it) {
+                const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
+                const int a = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&sm.full[s], ph);
+                mbar_wait(&sm.acc_empty[a], aph ^ 1u);
+                tc_fence_after();
+                const uint64_t bdesc = umma_desc_sw128(sm.b[s]);
+                for (int h = 0; h < halves; ++h) {
+                    const uint32_t d = tmem_base + (uint32_t)((a * 2 + h) * TC_BN);
+                    const uint64_t ad = h ? adesc1 : adesc0;
+#pragma unroll
+                    for (int k = 0; k < TC_D / 8; ++k)               // +32 bytes (2 x 16 B) per K step inside the swizzle atom
+                        umma_tf32(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+                }
+                umma_commit(&sm.empty[s]);
+                umma_commit(&sm.acc_full[a]);
+            }
+        }
+    } else if (warp - 2 < 4 * halves) {
+        // ================= epilogue: one thread per own row =================
+        const int q = warp & 3;                                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                             // which M = 128 accumulator
+        const int r = half * 128 + q * 32 + lane;                     // row inside the CTA tile
+        const int row = row0 + r;
+        const bool valid = row < M;
+        const float own_hn = valid ? hn_own[(size_t)p * pad_own + row] : 0.0f;
+        const float two_eps = 0.0078125f * sqrtf(fmaxf(-2.0f * own_hn, 0.0f) * fmaxf(str_max_sq, 0.0f)) + 1e-30f;   // 2 * 2^-8 |a| max|b|
+        float m_run = -INFINITY; int cnt = 0; bool overflow = false;
+
+        for (int it = 0; it < ntiles; ++it) {
+            const int a = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+            mbar_wait(&sm.acc_full[a], aph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < TC_BN / 32; ++c) {
+                float v[32];
+                __syncwarp();
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((a * 2 + half) * TC_BN + c * 32), v);
+                const int colbase = it * TC_BN + c * 32;              // CTA-local streamed column of v[0]
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 h = *reinterpret_cast<const float4*>(&sm.hn[colbase + 4 * c4]);
+                    f32x2 lo = add2(pack2(v[4 * c4], v[4 * c4 + 1]), pack2(h.x, h.y)), hi = add2(pack2(v[4 * c4 + 2], v[4 * c4 + 3]), pack2(h.z, h.w));
+                    unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
+                }
+                float m8[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    m8[k] = fmaxf(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], max3(v[8 * k + 5], v[8 * k + 6], v[8 * k + 7])));
+                m_run = fmaxf(m_run, fmaxf(max3(m8[0], m8[1], m8[2]), m8[3]));
+                const float thr = m_run - two_eps;
+                if (cnt > TC_CAP - 4) {                               // rare: compact the list against the current band
+                    int n = 0;
+                    for (int k = 0; k < cnt; ++k) {
+                        const float val = sm.cv[k][r];
+                        if (val >= thr) { sm.cv[n][r] = val; sm.ci[n][r] = sm.ci[k][r]; ++n; }
+                    }
+                    cnt = n;
+                    if (cnt > TC_CAP - 4) { overflow = true; cnt = 0; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                         // predicated append of the 8-column groups inside the band
+                    if (m8[k] >= thr) { sm.cv[cnt][r] = m8[k]; sm.ci[cnt][r] = t_begin * TC_BN + colbase + 8 * k; ++cnt; }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+        }
+
+        // ---- exact FP32 re-check of the surviving groups (or of the whole row after an overflow) ---------------------------
+        if (valid) {
+            float4 own[8];
+            const float4* o4 = reinterpret_cast<const float4*>(x_own + (size_t)(oo + row) * TC_D);
+#pragma unroll
+            for (int k4 = 0; k4 < 8; ++k4) own[k4] = __ldg(o4 + k4);
+            float best = -INFINITY; int best_j = 0x7fffffff;
+            const float thr = m_run - two_eps;
+            const int j_end = min(N, t_end * TC_BN);
+            if (!overflow) {
+                for (int k = 0; k < cnt; ++k) {
+                    if (sm.cv[k][r] < thr) continue;
+                    const int j0 = sm.ci[k][r];
+                    for (int j = j0; j < min(j0 + TC_SUB, j_end); ++j) {
+                        const float e = exact_score<COLDIR>(own, own_hn, x_str + (size_t)(os + j) * TC_D, hn_str_p[j]);
+                        if (e > best || (e == best && j < best_j)) { best = e; best_j = j; }
+                    }
+                }
+            } else {
+                for (int j = t_begin * TC_BN; j < j_end; ++j) {
+                    const float e = exact_score<COLDIR>(own, own_hn, x_str + (size_t)(os + j) * TC_D, hn_str_p[j]);
+                    if (e > best) { best = e; best_j = j; }
+                }
+            }
+            if (best_j != 0x7fffffff)
+                red_max_u64(out_packed + (size_t)p * pad_own + row, pack_best(float_key(best), (uint32_t)best_j));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_map(CUtensorMap* map, const float* base, long long rows, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = { (cuuint64_t)TC_D, (cuuint64_t)rows };
+    cuuint64_t strides[1] = { (cuuint64_t)TC_D * 4 };
+    cuuint32_t box[2] = { (cuuint32_t)TC_D, (cuuint32_t)box_rows };
+    cuuint32_t estr[2] = { 1, 1 };
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool k1_tc_supported(int D, long long total_M, long long total_N) { return D == TC_D && total_M > 0 && total_N > 0 && encode_fn() != nullptr; }
+
+// both directions; hna/hnb/row_packed/col_packed are the (prepared, zeroed) workspace arrays of k1_launch
+cudaError_t k1_tc_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+                         long long total_M, long long total_N, const float* hna, const float* hnb, int padM, int padN,
+                         unsigned long long* row_packed, unsigned long long* col_packed, cudaStream_t stream)
+{
+    CUtensorMap ms_own, ms_str, mt_own, mt_str;
+    if (!make_map(&ms_own, src, total_M, TC_BM) || !make_map(&ms_str, src, total_M, TC_BN) ||
+        !make_map(&mt_own, tgt, total_N, TC_BM) || !make_map(&mt_str, tgt, total_N, TC_BN)) return cudaErrorNotSupported;
+    const size_t smem = sizeof(TcSmem) + 1024;
+    static bool once = false;
+    if (!once) {
+        cudaError_t e = cudaFuncSetAttribute(k1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        once = true;
+    }
+    {   // src rows own, tgt streamed -> row_packed
+        const int tiles = (max_N + TC_BN - 1) / TC_BN, splits = (tiles + TC_MAX_TILES - 1) / TC_MAX_TILES;
+        dim3 grid((unsigned)((max_M + TC_BM - 1) / TC_BM), (unsigned)(splits > 0 ? splits : 1), (unsigned)P);
+        k1_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(ms_own, mt_str, src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, (int)grid.y);
+    }
+    {   // tgt rows own, src streamed -> col_packed
+        const int tiles = (max_M + TC_BN - 1) / TC_BN, splits = (tiles + TC_MAX_TILES - 1) / TC_MAX_TILES;
+        dim3 grid((unsigned)((max_N + TC_BM - 1) / TC_BM), (unsigned)(splits > 0 ? splits : 1), (unsigned)P);
+        k1_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mt_own, ms_str, tgt, src, tgt_off, src_off, hnb, hna, padN, padM, col_packed, (int)grid.y);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace bfr

@@ -38,6 +38,13 @@ extern "C" {
 int bfr_version(void);
 const char* bfr_error_string(int code);
 
+/* Process-wide tuning knobs.  BFR_CFG_K1_ALGO selects the mutual-NN implementation: 0 = FP32 FFMA2 kernel (every product
+ * in FP32), 1 = tensor-core (tcgen05 TF32) filter followed by an exact FP32 re-check of the near-best candidates.  Both
+ * produce bit-identical outputs. */
+#define BFR_CFG_K1_ALGO 1
+int bfr_config_set(int key, int value);
+int bfr_config_get(int key);
+
 /* ---- K1: fused L2 distance + mutual nearest neighbour -------------------------------------------------------------
  * Replaces buffer.mutual_matching (models/BUFFER.py:335-359) and its two knn_cuda.KNN(k=1) calls (:347, :352).
  * Outputs (each optional, may be NULL): nn_s[i] = nearest tgt row of src row i, nn_t[j] = nearest src row of tgt row
@@ -45,10 +52,10 @@ const char* bfr_error_string(int code);
  * p, ascending in s, written at s_mids[src_off[p] ...] with n_mutual[p] entries (models/BUFFER.py:356-357); corr_xyz =
  * the matched keypoints gathered into correspondence records at the same offsets (models/BUFFER.py:284,287; needs
  * src_xyz/tgt_xyz [rows][3]).  col_splits >= 1 splits the target rows of each pair over that many CTAs (use > 1 when P
- * is too small to fill 148 SMs). */
+ * is too small to fill 148 SMs).  total_M / total_N = rows of the concatenated descriptor arrays (TMA tensor-map bounds). */
 size_t bfr_mutual_nn_workspace_bytes(int P, int max_M, int max_N);
 int bfr_mutual_matching_batched(const float* src_des, const float* tgt_des, const int32_t* src_off, const int32_t* tgt_off,
-                                int P, int max_M, int max_N, int D, int col_splits,
+                                int P, int max_M, int max_N, int total_M, int total_N, int D, int col_splits,
                                 int64_t* nn_s, int64_t* nn_t, float* dist_s, float* dist_t,
                                 const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr_xyz,
                                 void* ws, size_t ws_bytes, void* stream);

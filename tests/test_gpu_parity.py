@@ -15,8 +15,16 @@ def _pairs(P, N, **kw):
     return S.make_pairs(P, N, **kw)
 
 
+@pytest.fixture(params=[0, 1], ids=["k1_fp32", "k1_tensor_filter"])
+def algo(request, backend):
+    """run the test with both mutual-NN implementations (FP32 FFMA2 kernel / tcgen05 filter + exact re-check)"""
+    backend.set_k1_algo(request.param)
+    yield request.param
+    backend.set_k1_algo(0)
+
+
 @pytest.mark.parametrize("M,N", [(1, 1), (3, 5), (64, 64), (65, 63), (511, 513), (512, 512), (700, 1300), (2500, 1500)])
-def test_mutual_nn_bit_exact_ragged(oracle, backend, M, N):
+def test_mutual_nn_bit_exact_ragged(oracle, backend, algo, M, N):
     g = torch.Generator().manual_seed(M * 10007 + N)
     src = torch.nn.functional.normalize(torch.randn(M, 32, generator=g), dim=-1)
     tgt = torch.nn.functional.normalize(torch.randn(N, 32, generator=g), dim=-1)
@@ -38,7 +46,7 @@ def test_mutual_nn_bit_exact_ragged(oracle, backend, M, N):
     assert s2.dtype == np.int64 and np.array_equal(s2, s) and np.array_equal(t2, t)
 
 
-def test_mutual_nn_unnormalised_and_splits(oracle, backend):
+def test_mutual_nn_unnormalised_and_splits(oracle, backend, algo):
     g = torch.Generator().manual_seed(5)
     src = torch.randn(900, 32, generator=g) * torch.rand(900, 1, generator=g) * 3
     tgt = torch.randn(1100, 32, generator=g) * torch.rand(1100, 1, generator=g) * 3
@@ -50,7 +58,7 @@ def test_mutual_nn_unnormalised_and_splits(oracle, backend):
         assert np.array_equal(r["nn_t"].cpu().numpy(), nn_t), splits
 
 
-def test_mutual_matching_batched_varlen(oracle, backend):
+def test_mutual_matching_batched_varlen(oracle, backend, algo):
     sizes = [(300, 200), (1, 7), (1025, 513), (64, 640), (5, 5)]
     g = torch.Generator().manual_seed(11)
     srcs = [torch.nn.functional.normalize(torch.randn(m, 32, generator=g), dim=-1) for m, _ in sizes]
@@ -187,7 +195,7 @@ def test_post_refinement_bit_exact(oracle, backend):
         assert it_o >= 1 and inl_o > 300
 
 
-def test_register_pipeline_matches_oracle_and_recovers_pose(oracle, backend):
+def test_register_pipeline_matches_oracle_and_recovers_pose(oracle, backend, algo):
     P, N, H = 6, 1200, 8000
     b = _pairs(P, N, cfg_id=17)
     off = np.arange(P + 1, dtype=np.int32) * N
@@ -207,7 +215,7 @@ def test_register_pipeline_matches_oracle_and_recovers_pose(oracle, backend):
     assert np.array_equal(Th.numpy(), To) and np.array_equal(nmh.numpy(), nm_o)
 
 
-def test_full_size_properties(backend):
+def test_full_size_properties(backend, algo):
     """config-2-sized pairs (5000 keypoints, 50k hypotheses): size-independent properties instead of the slow oracle"""
     P, N = 8, 5000
     b = _pairs(P, N, cfg_id=2).to(DEV)

@@ -9,6 +9,7 @@ N = int(sys.argv[3]) if len(sys.argv) > 3 else 5000
 L = C.CDLL(os.path.abspath(so))
 L.bfr_mutual_nn_workspace_bytes.restype = C.c_size_t
 dev = "cuda:0"
+if len(sys.argv) > 4: L.bfr_config_set(1, int(sys.argv[4]))
 g = torch.Generator(device=dev); g.manual_seed(1)
 src = torch.nn.functional.normalize(torch.randn(P * N, 32, device=dev, generator=g), dim=-1)
 tgt = torch.nn.functional.normalize(torch.randn(P * N, 32, device=dev, generator=g), dim=-1)
@@ -19,7 +20,7 @@ nn_s = torch.empty(P * N, dtype=torch.int64, device=dev); nn_t = torch.empty_lik
 nm = torch.empty(P, dtype=torch.int32, device=dev)
 vp = C.c_void_p
 def run():
-    rc = L.bfr_mutual_matching_batched(vp(src.data_ptr()), vp(tgt.data_ptr()), vp(off.data_ptr()), vp(off.data_ptr()), P, N, N, 32, 1,
+    rc = L.bfr_mutual_matching_batched(vp(src.data_ptr()), vp(tgt.data_ptr()), vp(off.data_ptr()), vp(off.data_ptr()), P, N, N, P * N, P * N, 32, 1,
                                        vp(nn_s.data_ptr()), vp(nn_t.data_ptr()), None, None, None, None, None, None, vp(nm.data_ptr()), None,
                                        vp(ws.data_ptr()), C.c_size_t(ws.numel()), vp(torch.cuda.current_stream().cuda_stream))
     assert rc == 0, rc

@@ -63,7 +63,8 @@ BFR_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint3
 BFR_DEVINL void umma_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 BFR_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 BFR_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-BFR_DEVINL void tmem_ld32(uint32_t taddr, float (&v)[32])
+// issue only; the registers become valid after tmem_ld_wait()
+BFR_DEVINL void tmem_ld32_issue(uint32_t taddr, float (&v)[32])
 {
     uint32_t r[32];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -73,9 +74,17 @@ BFR_DEVINL void tmem_ld32(uint32_t taddr, float (&v)[32])
                    "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
                    "=r"(r[30]), "=r"(r[31])
                  : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// wait for all outstanding tcgen05.ld of this thread; the buffer is threaded through as in/out so that no use is hoisted above
+BFR_DEVINL void tmem_ld_wait(float (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
+                   "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]),
+                   "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :: "memory");
 }
 
 // exact score of (own row, candidate row) — the oracle's chain.  COLDIR = the "own" side is the target set.
@@ -101,8 +110,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
              const float* __restrict__ hn_own, const float* __restrict__ hn_str, int pad_own, int pad_str,
              unsigned long long* __restrict__ out_packed, int splits)
 {
-    extern __shared__ unsigned char smem_raw[];
-    TcSmem& sm = *reinterpret_cast<TcSmem*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) unsigned char smem_raw[];      // no static shared memory in this kernel: base is 1024-aligned
+    TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();                 // SWIZZLE_128B atoms need 1024-byte alignment
 
     const int p = blockIdx.z;
     const int oo = off_own[p], M = off_own[p + 1] - oo;
@@ -195,45 +205,53 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         const float two_eps = 0.0078125f * sqrtf(fmaxf(-2.0f * own_hn, 0.0f) * fmaxf(str_max_sq, 0.0f)) + 1e-30f;   // 2 * 2^-8 |a| max|b|
         float m_run = -INFINITY; int cnt = 0; bool overflow = false;
 
+        // one 32-column chunk: add hn(b_j), 8-column group maxima, running maximum, predicated append of in-band groups
+        auto process = [&](float (&v)[32], int colbase) {
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 h = *reinterpret_cast<const float4*>(&sm.hn[colbase + 4 * c4]);
+                f32x2 lo = add2(pack2(v[4 * c4], v[4 * c4 + 1]), pack2(h.x, h.y)), hi = add2(pack2(v[4 * c4 + 2], v[4 * c4 + 3]), pack2(h.z, h.w));
+                unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
+            }
+            float m8[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                m8[k] = fmaxf(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], max3(v[8 * k + 5], v[8 * k + 6], v[8 * k + 7])));
+            m_run = fmaxf(m_run, fmaxf(max3(m8[0], m8[1], m8[2]), m8[3]));
+            const float thr = m_run - two_eps;
+            if (cnt > TC_CAP - 4) {                                   // rare: compact the list against the current band
+                int n = 0;
+                for (int k = 0; k < cnt; ++k) {
+                    const float val = sm.cv[k][r];
+                    if (val >= thr) { sm.cv[n][r] = val; sm.ci[n][r] = sm.ci[k][r]; ++n; }
+                }
+                cnt = n;
+                if (cnt > TC_CAP - 4) { overflow = true; cnt = 0; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                             // predicated append of the 8-column groups inside the band
+                if (m8[k] >= thr) { sm.cv[cnt][r] = m8[k]; sm.ci[cnt][r] = t_begin * TC_BN + colbase + 8 * k; ++cnt; }
+            }
+        };
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int it = 0; it < ntiles; ++it) {
             const int a = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
             mbar_wait(&sm.acc_full[a], aph);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < TC_BN / 32; ++c) {
-                float v[32];
-                __syncwarp();
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((a * 2 + half) * TC_BN + c * 32), v);
-                const int colbase = it * TC_BN + c * 32;              // CTA-local streamed column of v[0]
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 h = *reinterpret_cast<const float4*>(&sm.hn[colbase + 4 * c4]);
-                    f32x2 lo = add2(pack2(v[4 * c4], v[4 * c4 + 1]), pack2(h.x, h.y)), hi = add2(pack2(v[4 * c4 + 2], v[4 * c4 + 3]), pack2(h.z, h.w));
-                    unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
-                }
-                float m8[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    m8[k] = fmaxf(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], max3(v[8 * k + 5], v[8 * k + 6], v[8 * k + 7])));
-                m_run = fmaxf(m_run, fmaxf(max3(m8[0], m8[1], m8[2]), m8[3]));
-                const float thr = m_run - two_eps;
-                if (cnt > TC_CAP - 4) {                               // rare: compact the list against the current band
-                    int n = 0;
-                    for (int k = 0; k < cnt; ++k) {
-                        const float val = sm.cv[k][r];
-                        if (val >= thr) { sm.cv[n][r] = val; sm.ci[n][r] = sm.ci[k][r]; ++n; }
-                    }
-                    cnt = n;
-                    if (cnt > TC_CAP - 4) { overflow = true; cnt = 0; }
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {                         // predicated append of the 8-column groups inside the band
-                    if (m8[k] >= thr) { sm.cv[cnt][r] = m8[k]; sm.ci[cnt][r] = t_begin * TC_BN + colbase + 8 * k; ++cnt; }
-                }
-            }
-            tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+            const uint32_t t0 = lane_base + (uint32_t)((a * 2 + half) * TC_BN);
+            const int cb = it * TC_BN;                                // CTA-local streamed column of this tile
+            float va[32], vb[32];                                     // software pipeline: load chunk c+1 while chunk c is processed
+            tmem_ld32_issue(t0, va);      tmem_ld_wait(va);
+            tmem_ld32_issue(t0 + 32, vb); process(va, cb);      tmem_ld_wait(vb);
+            __syncwarp();
+            tmem_ld32_issue(t0 + 64, va); process(vb, cb + 32); tmem_ld_wait(va);
+            __syncwarp();
+            tmem_ld32_issue(t0 + 96, vb); process(va, cb + 64); tmem_ld_wait(vb);
+            tc_fence_before();                                        // all TMEM reads of this accumulator are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[a]);             // the MMA warp may overwrite it while the last chunk is processed
+            process(vb, cb + 96);
         }
 
         // ---- exact FP32 re-check of the surviving groups (or of the whole row after an overflow) ---------------------------
@@ -249,9 +267,19 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                 for (int k = 0; k < cnt; ++k) {
                     if (sm.cv[k][r] < thr) continue;
                     const int j0 = sm.ci[k][r];
-                    for (int j = j0; j < min(j0 + TC_SUB, j_end); ++j) {
-                        const float e = exact_score<COLDIR>(own, own_hn, x_str + (size_t)(os + j) * TC_D, hn_str_p[j]);
-                        if (e > best || (e == best && j < best_j)) { best = e; best_j = j; }
+#pragma unroll 1
+                    for (int jb = j0; jb < min(j0 + TC_SUB, j_end); jb += 4) {
+                        float e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {                 // 4 independent exact chains in flight (padding rows re-read column jb)
+                            const int j = (jb + u < j_end) ? jb + u : jb;
+                            e[u] = exact_score<COLDIR>(own, own_hn, x_str + (size_t)(os + j) * TC_D, hn_str_p[j]);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int j = jb + u;
+                            if (j < j_end && (e[u] > best || (e[u] == best && j < best_j))) { best = e[u]; best_j = j; }
+                        }
                     }
                 }
             } else {

@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config id (1-5); 2 is the one the metric is quoted on")
     ap.add_argument("--pairs", type=int, default=0, help="override the number of pairs per GPU (0 = the config's)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU baseline sample (0 = 4 per host thread)")
+    ap.add_argument("--k1-algo", type=int, default=1, help="0 = FP32 FFMA2 mutual-NN kernel, 1 = tcgen05 TF32 filter + exact FP32 re-check (bit-identical results)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -185,6 +186,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from buffer_b200 import _lib, backend as B
     L = _lib.lib()
+    B.set_k1_algo(args.k1_algo)
 
     c, P = workload(args.config, args.pairs)
     N = c["gen"]["num_kpts"]

@@ -187,20 +187,24 @@ BFR_DEVINL float resid2(const float R[9], const float t[3], float sx, float sy, 
 }
 
 // One RANSAC hypothesis (Open3D 0.13 iteration as called at models/BUFFER.py:318-324; see oracle/bfr_oracle.c
-// orc_hypothesis for the line-by-line statement).  corr: K records of 8 floats {sx sy sz 0 qx qy qz 0}.
-BFR_DEVINL bool make_hypothesis(const float4* __restrict__ corr, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h,
-                                float dist_th2, float sim_th2, float R[9], float t[3])
+// orc_hypothesis for the line-by-line statement), split in two stages so that the kernel can compact between them.
+// corr: K records of 8 floats {sx sy sz 0 qx qy qz 0}.
+BFR_DEVINL void load_sample(const float4* __restrict__ corr, const uint32_t id[3], float s[3][3], float q[3][3])
 {
-    uint32_t id[3];
-    sample3(seed, pair_id, h, K, id);
-    if (id[0] == id[1] || id[0] == id[2] || id[1] == id[2]) return false;
-    float s[3][3], q[3][3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         const float4 a = __ldg(&corr[2 * (size_t)id[i]]), b = __ldg(&corr[2 * (size_t)id[i] + 1]);
         s[i][0] = a.x; s[i][1] = a.y; s[i][2] = a.z; q[i][0] = b.x; q[i][1] = b.y; q[i][2] = b.z;
     }
-    // CorrespondenceCheckerBasedOnEdgeLength on squared lengths, pairs (0,1),(0,2),(1,2)
+}
+// stage 1 (cheap, every hypothesis): Philox sample, repeated-index rejection, CorrespondenceCheckerBasedOnEdgeLength on
+// squared lengths of the pairs (0,1),(0,2),(1,2)
+BFR_DEVINL bool hypothesis_precheck(const float4* __restrict__ corr, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h, float sim_th2,
+                                    uint32_t id[3], float s[3][3], float q[3][3])
+{
+    sample3(seed, pair_id, h, K, id);
+    if (id[0] == id[1] || id[0] == id[2] || id[1] == id[2]) return false;
+    load_sample(corr, id, s, q);
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
         const int a = (e == 2) ? 1 : 0, b = (e == 0) ? 1 : 2;
@@ -210,6 +214,11 @@ BFR_DEVINL bool make_hypothesis(const float4* __restrict__ corr, uint32_t K, uin
         const float dt2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
         if (ds2 < __fmul_rn(dt2, sim_th2) || dt2 < __fmul_rn(ds2, sim_th2)) return false;
     }
+    return true;
+}
+// stage 2 (survivors of stage 1): 3-point Kabsch + CorrespondenceCheckerBasedOnDistance on the three samples
+BFR_DEVINL bool hypothesis_fit(const float s[3][3], const float q[3][3], float dist_th2, float R[9], float t[3])
+{
     const float third = 0.33333334f;
     float cs[3], cq[3], Hm[9];
 #pragma unroll
@@ -230,11 +239,17 @@ BFR_DEVINL bool make_hypothesis(const float4* __restrict__ corr, uint32_t K, uin
 #pragma unroll
     for (int r = 0; r < 3; ++r)
         t[r] = __fsub_rn(cq[r], __fmaf_rn(R[3 * r + 2], cs[2], __fmaf_rn(R[3 * r + 1], cs[1], __fmul_rn(R[3 * r + 0], cs[0]))));
-    // CorrespondenceCheckerBasedOnDistance on the three samples
 #pragma unroll
     for (int i = 0; i < 3; ++i)
         if (resid2(R, t, s[i][0], s[i][1], s[i][2], q[i][0], q[i][1], q[i][2]) > dist_th2) return false;
     return true;
+}
+BFR_DEVINL bool make_hypothesis(const float4* __restrict__ corr, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h,
+                                float dist_th2, float sim_th2, float R[9], float t[3])
+{
+    uint32_t id[3]; float s[3][3], q[3][3];
+    if (!hypothesis_precheck(corr, K, seed, pair_id, h, sim_th2, id, s, q)) return false;
+    return hypothesis_fit(s, q, dist_th2, R, t);
 }
 
 }  // namespace bfr

@@ -5,10 +5,11 @@
 // scoring block (models/BUFFER.py:303-311).  Semantics and exact arithmetic: oracle/bfr_oracle.c (orc_hypothesis,
 // orc_count_inliers, orc_ransac, orc_score_hypotheses); DESIGN.md §K2/§K3.
 //
-// Structure: one CTA owns a contiguous range of hypothesis indices of one pair.  Every thread generates one
-// hypothesis per round (Philox counter = (h, pair_id, 0, 0)), runs the edge-length check, the 3-point Kabsch and the
-// distance check, and survivors (a few %) are appended to a shared-memory queue.  Whenever the queue holds a full
-// block's worth, each thread takes one surviving hypothesis and scores it against ALL correspondences, which stream
+// Structure: one CTA owns a contiguous range of hypothesis indices of one pair.  Every thread draws one hypothesis per
+// round (Philox counter = (h, pair_id, 0, 0)) and runs the cheap checks (repeated index, edge lengths); survivors (~10 %)
+// are compacted into queue 1 so that the 3-point Kabsch + distance check runs on dense warps; what passes (a few %) goes
+// to queue 2.  Whenever queue 2 holds a full block's worth, each thread takes one hypothesis and scores it against ALL
+// correspondences, which stream
 // through shared memory in 2048-correspondence chunks laid out pair-interleaved so that the transform is FFMA2
 // (two correspondences per instruction) with warp-uniform LDS.128 broadcasts.  The inlier count never leaves the
 // thread; the CTA's best (count << 32 | ~h) goes out with one 64-bit atomicMax.
@@ -24,8 +25,10 @@ constexpr int RS_QCAP = 2 * RS_THREADS;
 
 struct __align__(16) RsSmem {
     float4 chunk[RS_CHUNK / 2][4];              // per pair of correspondences: (sx sx' sy sy')(sz sz' qx qx')(qy qy' qz qz')(w w' - -)
-    float q[12][RS_QCAP];                       // queued survivors: R (9) + t (3), SoA
+    float q[12][RS_QCAP];                       // queue 2: hypotheses that passed every check: R (9) + t (3), SoA
     uint32_t qh[RS_QCAP];
+    uint4 q1[RS_QCAP];                          // queue 1: survivors of the cheap checks: {h, i0, i1, i2}
+    int q1count;
     unsigned long long red[RS_THREADS / 32];
     int qcount;
 };
@@ -123,15 +126,23 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
     const uint32_t pair_id = pair_id_base + (uint32_t)p;
     const int lane = threadIdx.x & 31;
 
-    if (threadIdx.x == 0) sm.qcount = 0;
+    if (threadIdx.x == 0) { sm.qcount = 0; sm.q1count = 0; }
     __syncthreads();
     unsigned long long best = 0ull;
 
-    for (uint32_t base = hb; base < he; base += RS_THREADS) {
-        const uint32_t h = base + threadIdx.x;
+    // stage 2 on n queue-1 entries (thread i takes entry i): Kabsch + distance check on dense warps, survivors -> queue 2;
+    // scores a full block of queue 2 whenever one is available
+    auto fit_queue1 = [&](int n) {
         float R[9], t[3];
-        bool ok = false;
-        if (h < he) ok = make_hypothesis(corr_p, (uint32_t)K, seed, pair_id, h, d2max, sim2, R, t);
+        bool ok = false; uint32_t h = 0;
+        if ((int)threadIdx.x < n) {
+            const uint4 e = sm.q1[threadIdx.x];
+            h = e.x;
+            const uint32_t id[3] = { e.y, e.z, e.w };
+            float s[3][3], q[3][3];
+            load_sample(corr_p, id, s, q);
+            ok = hypothesis_fit(s, q, d2max, R, t);
+        }
         const unsigned bal = __ballot_sync(0xffffffffu, ok);
         if (bal) {
             int pos = 0;
@@ -147,11 +158,10 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         }
         __syncthreads();
         const int qn = sm.qcount;
-        __syncthreads();                       // everyone has read qcount before the next round's atomicAdd
+        __syncthreads();
         if (qn >= RS_THREADS) {
             score_queue(sm, corr_p, K, RS_THREADS, d2max, best);
-            // move the overflow [RS_THREADS, qn) down to the front
-            const int rem = qn - RS_THREADS;
+            const int rem = qn - RS_THREADS;                           // move the overflow [RS_THREADS, qn) down to the front
             float mv[12]; uint32_t mh = 0;
             if ((int)threadIdx.x < rem) {
 #pragma unroll
@@ -167,6 +177,39 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
             if (threadIdx.x == 0) sm.qcount = rem;
             __syncthreads();
         }
+    };
+
+    for (uint32_t base = hb; base < he; base += RS_THREADS) {
+        // stage 1: one hypothesis per thread, cheap checks only (~10 % survive at 70 % outliers)
+        const uint32_t h = base + threadIdx.x;
+        uint32_t id[3] = { 0u, 0u, 0u };
+        bool ok = false;
+        if (h < he) { float s[3][3], q[3][3]; ok = hypothesis_precheck(corr_p, (uint32_t)K, seed, pair_id, h, sim2, id, s, q); }
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (bal) {
+            int pos = 0;
+            if (lane == 0) pos = atomicAdd(&sm.q1count, __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+            if (ok) sm.q1[pos] = make_uint4(h, id[0], id[1], id[2]);
+        }
+        __syncthreads();
+        const int n1 = sm.q1count;
+        __syncthreads();                       // everyone has read q1count before it changes
+        if (n1 >= RS_THREADS) {
+            fit_queue1(RS_THREADS);
+            const int rem = n1 - RS_THREADS;
+            uint4 mv = make_uint4(0u, 0u, 0u, 0u);
+            if ((int)threadIdx.x < rem) mv = sm.q1[RS_THREADS + threadIdx.x];
+            __syncthreads();
+            if ((int)threadIdx.x < rem) sm.q1[threadIdx.x] = mv;
+            if (threadIdx.x == 0) sm.q1count = rem;
+            __syncthreads();
+        }
+    }
+    {
+        const int n1 = sm.q1count;             // flush queue 1, then queue 2
+        __syncthreads();
+        if (n1 > 0) fit_queue1(n1);
     }
     const int qn = sm.qcount;
     if (qn > 0) score_queue(sm, corr_p, K, qn, d2max, best);

@@ -22,6 +22,7 @@
 #include "bfr_kernels.h"
 #include <cuda.h>
 #include <cmath>
+#include <type_traits>
 
 namespace bfr {
 
@@ -41,7 +42,7 @@ struct TcSmem {
     float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
     float cv[TC_CAP][TC_BM];                    // candidate group maxima (approximate scores)  [slot][row]
     int ci[TC_CAP][TC_BM];                      // first streamed column of the candidate group
-    float red[TC_THREADS / 32];
+    float red[TC_THREADS / 32], red2[TC_THREADS / 32];
     uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
@@ -140,22 +141,23 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    float hmin = 0.0f;
+    float hmin = 0.0f, hmax = -INFINITY;
     for (int i = threadIdx.x; i < ntiles * TC_BN; i += TC_THREADS) {
         const float h = hn_str_p[t_begin * TC_BN + i];               // padded array: -inf beyond N
         sm.hn[i] = h;
-        if (h > -INFINITY) hmin = fminf(hmin, h);
+        if (h > -INFINITY) { hmin = fminf(hmin, h); hmax = fmaxf(hmax, h); }
     }
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) hmin = fminf(hmin, __shfl_xor_sync(0xffffffffu, hmin, o));
-    if (lane == 0) sm.red[warp] = hmin;
+    for (int o = 16; o >= 1; o >>= 1) { hmin = fminf(hmin, __shfl_xor_sync(0xffffffffu, hmin, o)); hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o)); }
+    if (lane == 0) { sm.red[warp] = hmin; sm.red2[warp] = hmax; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
 #pragma unroll
-    for (int w = 0; w < TC_THREADS / 32; ++w) hmin = fminf(hmin, sm.red[w]);
+    for (int w = 0; w < TC_THREADS / 32; ++w) { hmin = fminf(hmin, sm.red[w]); hmax = fmaxf(hmax, sm.red2[w]); }
     const float str_max_sq = -2.0f * hmin;                            // max_j |b_j|^2 over this CTA's columns
+    const float hn_spread = fmaxf(hmax - hmin, 0.0f);                 // 0 for exactly normalised descriptors
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -203,22 +205,31 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         const bool valid = row < M;
         const float own_hn = valid ? hn_own[(size_t)p * pad_own + row] : 0.0f;
         const float two_eps = 0.0078125f * sqrtf(fmaxf(-2.0f * own_hn, 0.0f) * fmaxf(str_max_sq, 0.0f)) + 1e-30f;   // 2 * 2^-8 |a| max|b|
+        // Streamed norms (nearly) uniform -- L2-normalised descriptors, BUFFER's case: rank full tiles on the raw dot products
+        // (no hn add) and widen the band by the spread of hn; m_run then lives in "dot + hmax" units so both kinds of tile compare.
+        const bool uniform = hn_spread <= 0.0009765625f * str_max_sq;   // CTA-uniform (the branch below contains warp-collective TMEM loads)
+        const float band = uniform ? two_eps + hn_spread : two_eps;
         float m_run = -INFINITY; int cnt = 0; bool overflow = false;
 
         // one 32-column chunk: add hn(b_j), 8-column group maxima, running maximum, predicated append of in-band groups
-        auto process = [&](float (&v)[32], int colbase) {
+        auto process = [&](float (&v)[32], int colbase, auto raw_tag) {
+            constexpr bool RAW = decltype(raw_tag)::value;            // RAW: v stays the bare dot product, compared in "dot + hmax" units
+            if (!RAW) {
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                const float4 h = *reinterpret_cast<const float4*>(&sm.hn[colbase + 4 * c4]);
-                f32x2 lo = add2(pack2(v[4 * c4], v[4 * c4 + 1]), pack2(h.x, h.y)), hi = add2(pack2(v[4 * c4 + 2], v[4 * c4 + 3]), pack2(h.z, h.w));
-                unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 h = *reinterpret_cast<const float4*>(&sm.hn[colbase + 4 * c4]);
+                    f32x2 lo = add2(pack2(v[4 * c4], v[4 * c4 + 1]), pack2(h.x, h.y)), hi = add2(pack2(v[4 * c4 + 2], v[4 * c4 + 3]), pack2(h.z, h.w));
+                    unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
+                }
             }
             float m8[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < 4; ++k) {
                 m8[k] = fmaxf(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], max3(v[8 * k + 5], v[8 * k + 6], v[8 * k + 7])));
+                if (RAW) m8[k] += hmax;
+            }
             m_run = fmaxf(m_run, fmaxf(max3(m8[0], m8[1], m8[2]), m8[3]));
-            const float thr = m_run - two_eps;
+            const float thr = m_run - band;
             if (cnt > TC_CAP - 4) {                                   // rare: compact the list against the current band
                 int n = 0;
                 for (int k = 0; k < cnt; ++k) {
@@ -242,16 +253,25 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             const uint32_t t0 = lane_base + (uint32_t)((a * 2 + half) * TC_BN);
             const int cb = it * TC_BN;                                // CTA-local streamed column of this tile
             float va[32], vb[32];                                     // software pipeline: load chunk c+1 while chunk c is processed
+            const bool raw = uniform && (t_begin + it + 1) * TC_BN <= N;   // full tile (no padding columns to mask) and uniform norms
             tmem_ld32_issue(t0, va);      tmem_ld_wait(va);
-            tmem_ld32_issue(t0 + 32, vb); process(va, cb);      tmem_ld_wait(vb);
-            __syncwarp();
-            tmem_ld32_issue(t0 + 64, va); process(vb, cb + 32); tmem_ld_wait(va);
-            __syncwarp();
-            tmem_ld32_issue(t0 + 96, vb); process(va, cb + 64); tmem_ld_wait(vb);
+            if (raw) {
+                tmem_ld32_issue(t0 + 32, vb); process(va, cb, std::true_type{});      tmem_ld_wait(vb);
+                __syncwarp();
+                tmem_ld32_issue(t0 + 64, va); process(vb, cb + 32, std::true_type{}); tmem_ld_wait(va);
+                __syncwarp();
+                tmem_ld32_issue(t0 + 96, vb); process(va, cb + 64, std::true_type{}); tmem_ld_wait(vb);
+            } else {
+                tmem_ld32_issue(t0 + 32, vb); process(va, cb, std::false_type{});      tmem_ld_wait(vb);
+                __syncwarp();
+                tmem_ld32_issue(t0 + 64, va); process(vb, cb + 32, std::false_type{}); tmem_ld_wait(va);
+                __syncwarp();
+                tmem_ld32_issue(t0 + 96, vb); process(va, cb + 64, std::false_type{}); tmem_ld_wait(vb);
+            }
             tc_fence_before();                                        // all TMEM reads of this accumulator are complete
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.acc_empty[a]);             // the MMA warp may overwrite it while the last chunk is processed
-            process(vb, cb + 96);
+            if (raw) process(vb, cb + 96, std::true_type{}); else process(vb, cb + 96, std::false_type{});
         }
 
         // ---- exact FP32 re-check of the surviving groups (or of the whole row after an overflow) ---------------------------
@@ -261,7 +281,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 #pragma unroll
             for (int k4 = 0; k4 < 8; ++k4) own[k4] = __ldg(o4 + k4);
             float best = -INFINITY; int best_j = 0x7fffffff;
-            const float thr = m_run - two_eps;
+            const float thr = m_run - band;
             const int j_end = min(N, t_end * TC_BN);
             if (!overflow) {
                 for (int k = 0; k < cnt; ++k) {

@@ -235,6 +235,24 @@ def main():
     T, nm, ni = out
     recall, rte, rre = S.registration_recall(T.cpu(), batch.T_gt.cpu())
 
+    # ---- extra leg (outside the timed region): the all-FP32 mutual-NN kernel on the same data, for the FP32 roofline --------
+    fp32_ms = None
+    if rank == 0:
+        B.set_k1_algo(B.K1_FP32)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+        for a_, b_ in ev:
+            a_.record(); b_.record()
+        for a_, b_ in ev:
+            L.bfr_debug_set_k1_events(ctypes.c_void_p(a_.cuda_event), ctypes.c_void_p(b_.cuda_event))
+            r_fp = B.mutual_matching_batched(src_des, tgt_des, off, off, N, N, want_nn=True, want_mids=False, col_splits=1)
+        L.bfr_debug_set_k1_events(None, None)
+        torch.cuda.synchronize()
+        fp32_ms = min(a_.elapsed_time(b_) for a_, b_ in ev)
+        B.set_k1_algo(args.k1_algo)
+        r_tc = B.mutual_matching_batched(src_des, tgt_des, off, off, N, N, want_nn=True, want_mids=False)
+        k1_paths_identical = bool(torch.equal(r_fp["nn_s"], r_tc["nn_s"]) and torch.equal(r_fp["nn_t"], r_tc["nn_t"]))
+        del r_fp, r_tc
+
     # ---- e2e: host (pinned) buffers -> poses on the host, copies inside the timed region ---------------------------
     e2e = None
     if not args.no_e2e:
@@ -259,27 +277,40 @@ def main():
         e2e = {"value": world * P * args.steps / tt.item(), "unit": UNIT,
                "h2d_bytes_per_step": int(sum(x.numel() * 4 for x in h)), "d2h_bytes_per_step": int(Th.numel() * 4 + nmh.numel() * 4 + nih.numel() * 4),
                "api": "buffer_b200.backend.HostRegistrar.run -> bfr_register_uniform_host (pinned host buffers, %d-pair chunks on 2 streams)" % chunk,
-               "poses_equal_device_path": same, "launches_per_step": 8 * ((P + chunk - 1) // chunk)}
+               "poses_equal_device_path": same, "launches_per_step": (9 if args.k1_algo == 1 else 8) * ((P + chunk - 1) // chunk)}
 
     if rank == 0:
         flops_k1 = 2.0 * N * N * 32 * P
         ach = flops_k1 / (k1_ms * 1e-3) * 1e-12
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "k1_tc_traffic.json" if args.k1_algo == 1 else "k1_traffic.json")
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        mp = _measured_peaks()
+        fp32_roof = {"kernel": "k1_mutual_nn_kernel (all products in FP32, FFMA2)", "bound": "fp32", "achieved": flops_k1 / (fp32_ms * 1e-3) * 1e-12,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": flops_k1 / (fp32_ms * 1e-3) * 1e-12 / peak_tf, "ms_per_launch": fp32_ms,
+                     "peak_source": "live FFMA2 (fma.rn.f32x2) issue-rate probe on this GPU; MEASURED_PEAKS.json has no FP32 figure "
+                                    "(theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s)",
+                     "outputs_identical_to_tensor_path": k1_paths_identical}
+        if args.k1_algo == 1:
+            tf32_peak = (mp.get("bf16_tflops") or 1590.0) / 2.0
+            roof = {"kernel": "k1_tc_kernel x2 (tcgen05 TF32 filter + exact FP32 re-check; src->tgt and tgt->src)", "bound": "tensor",
+                    "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
+                    "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step, "algorithmic_flops_per_launch": flops_k1,
+                    "executed_tensor_flops_per_launch": 2 * flops_k1,
+                    "peak_source": "TF32 dense = half of the measured cuBLAS bf16 burst peak in MEASURED_PEAKS.json (%s)" % ("measured" if mp.get("bf16_tflops") else "fallback 1.59 PF"),
+                    "note": "K = 32 makes this kernel epilogue-bound (TMEM -> register max-reduction), not MMA-bound; the algorithmic FLOP rate exceeds "
+                            "the FP32 roofline because the products run on tensor cores and only near-best candidates are re-evaluated in FP32",
+                    "vs_fp32_ffma2_peak": ach / peak_tf, "hbm_peak_gbs_measured": mp.get("hbm_gbs")}
+        else:
+            roof = dict(fp32_roof, traffic=traffic, k1_ms_per_launch=k1_ms, k1_share_of_step=k1_ms / ms_step, algorithmic_flops_per_launch=flops_k1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args, c, P), "clocks": clocks, "gpu_launches": 7 * args.steps,
-                "roofline": {"kernel": "k1_mutual_nn_kernel", "bound": "fp32", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
-                             "traffic": traffic, "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step,
-                             "algorithmic_flops_per_launch": flops_k1,
-                             "peak_source": "live FFMA2 (fma.rn.f32x2) issue-rate probe on this GPU; MEASURED_PEAKS.json has no FP32 figure "
-                                            "(theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s)",
-                             "hbm_peak_gbs_measured": _measured_hbm()},
+                "config": config_dict(args, c, P), "clocks": clocks, "gpu_launches": (8 if args.k1_algo == 1 else 7) * args.steps,
+                "roofline": roof, "roofline_fp32_path": fp32_roof,
                 "quality": {"registration_recall": recall, "rte_max_m": float(rte.max()), "rre_max_deg": float(rre.max()),
                             "mutual_matches_mean": float(nm.float().mean()), "ransac_inliers_mean": float(ni.float().mean())}}
         if e2e is not None:
@@ -299,11 +330,11 @@ def main():
         dist.destroy_process_group()
 
 
-def _measured_hbm():
+def _measured_peaks():
     try:
-        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs")
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
-        return None
+        return {}
 
 
 if __name__ == "__main__":

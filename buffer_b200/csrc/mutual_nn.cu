@@ -342,7 +342,7 @@ size_t k1_workspace_bytes(int P, int max_M, int max_N)
     return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long)) + 256;
 }
 
-static int g_k1_algo = 0;                       // 0 = FP32 FFMA2 kernel, 1 = tensor-core filter + exact re-check (mutual_nn_tc.cu)
+static int g_k1_algo = 1;                       // 0 = FP32 FFMA2 kernel, 1 = tensor-core filter + exact re-check (mutual_nn_tc.cu)
 void k1_set_algo(int algo) { g_k1_algo = algo; }
 int k1_get_algo() { return g_k1_algo; }
 

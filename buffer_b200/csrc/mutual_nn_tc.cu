@@ -22,6 +22,7 @@
 #include "bfr_kernels.h"
 #include <cuda.h>
 #include <cmath>
+#include <cstdio>
 #include <type_traits>
 
 namespace bfr {
@@ -129,6 +130,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* hn_str_p = hn_str + (size_t)p * pad_str;
+#ifdef TC_TIMING
+    long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+#endif
 
     // ---- setup: barriers, TMEM, streamed half-norms (+ their minimum = largest streamed norm) ----------------------
     if (threadIdx.x == 0) {
@@ -158,6 +162,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     for (int w = 0; w < TC_THREADS / 32; ++w) { hmin = fminf(hmin, sm.red[w]); hmax = fmaxf(hmax, sm.red2[w]); }
     const float str_max_sq = -2.0f * hmin;                            // max_j |b_j|^2 over this CTA's columns
     const float hn_spread = fmaxf(hmax - hmin, 0.0f);                 // 0 for exactly normalised descriptors
+#ifdef TC_TIMING
+    tq1 = clock64();
+#endif
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -274,6 +281,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             if (raw) process(vb, cb + 96, std::true_type{}); else process(vb, cb + 96, std::false_type{});
         }
 
+#ifdef TC_TIMING
+        tq2 = clock64();
+#endif
         // ---- exact FP32 re-check of the surviving groups (or of the whole row after an overflow) ---------------------------
         if (valid) {
             float4 own[8];
@@ -284,8 +294,14 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             const float thr = m_run - band;
             const int j_end = min(N, t_end * TC_BN);
             if (!overflow) {
-                for (int k = 0; k < cnt; ++k) {
-                    if (sm.cv[k][r] < thr) continue;
+                int n = 0;                                            // compact the survivors so that the warp's lanes stay aligned
+                for (int k = 0; k < cnt; ++k)
+                    if (sm.cv[k][r] >= thr) { sm.ci[n][r] = sm.ci[k][r]; ++n; }
+#ifdef TC_TIMING
+                { long long tz = clock64(); int nmx = __reduce_max_sync(0xffffffffu, n), cmx = __reduce_max_sync(0xffffffffu, cnt), nsum = __reduce_add_sync(0xffffffffu, n);
+                  if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && warp == 2) printf("verify: own+compact %lld cycles, cnt max %d, n max %d, n sum %d\n", tz - tq2, cmx, nmx, nsum); }
+#endif
+                for (int k = 0; k < n; ++k) {
                     const int j0 = sm.ci[k][r];
 #pragma unroll 1
                     for (int jb = j0; jb < min(j0 + TC_SUB, j_end); jb += 4) {
@@ -313,8 +329,15 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         }
     }
 
+#ifdef TC_TIMING
+    tq3 = clock64();
+#endif
     tc_fence_before();
     __syncthreads();
+#ifdef TC_TIMING
+    tq4 = clock64();
+    if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && (warp == 2 || warp == 9)) printf("cta %d warp %d: setup %lld main %lld verify %lld tailwait %lld\n", blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq3 - tq2, tq4 - tq3);
+#endif
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 

@@ -20,7 +20,7 @@ def algo(request, backend):
     """run the test with both mutual-NN implementations (FP32 FFMA2 kernel / tcgen05 filter + exact re-check)"""
     backend.set_k1_algo(request.param)
     yield request.param
-    backend.set_k1_algo(0)
+    backend.set_k1_algo(1)
 
 
 @pytest.mark.parametrize("M,N", [(1, 1), (3, 5), (64, 64), (65, 63), (511, 513), (512, 512), (700, 1300), (2500, 1500)])

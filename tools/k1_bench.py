@@ -13,6 +13,10 @@ if len(sys.argv) > 4: L.bfr_config_set(1, int(sys.argv[4]))
 g = torch.Generator(device=dev); g.manual_seed(1)
 src = torch.nn.functional.normalize(torch.randn(P * N, 32, device=dev, generator=g), dim=-1)
 tgt = torch.nn.functional.normalize(torch.randn(P * N, 32, device=dev, generator=g), dim=-1)
+if len(sys.argv) > 5 and sys.argv[5] == "planted":      # every src row has a noisy copy at a permuted tgt row (the bench generator's structure)
+    noisy = torch.nn.functional.normalize(src + 0.05 * torch.randn(P * N, 32, device=dev, generator=g), dim=-1).reshape(P, N, 32)
+    perm = torch.argsort(torch.rand(P, N, device=dev, generator=g), dim=-1)
+    tgt = torch.empty_like(noisy).scatter_(1, perm[:, :, None].expand(P, N, 32), noisy).reshape(P * N, 32)
 off = (torch.arange(P + 1, dtype=torch.int32) * N).to(dev)
 nb = L.bfr_mutual_nn_workspace_bytes(P, N, N)
 ws = torch.empty(nb + 1024, dtype=torch.uint8, device=dev)

@@ -125,7 +125,7 @@ def cpu_baseline(c, sample_pairs, threads, b=None):
     (`b`: the first pairs of the GPU workload copied to the host, else freshly generated ones)"""
     from oracle import oracle as O
     O.build()
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    O.set_num_threads(threads)             # torchrun exports OMP_NUM_THREADS=1
     if b is None:
         b = S.make_pairs(sample_pairs, first_pair=0, **c["gen"])
     N = c["gen"]["num_kpts"]
@@ -145,7 +145,7 @@ def run_reference(args, rank, world):
         return
     c, P = workload(args.config, args.pairs)
     threads = os.cpu_count() or 1
-    sample = args.cpu_sample_pairs or max(threads * 2, 8)
+    sample = args.cpu_sample_pairs or max(threads * 8, 32)
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, _, _ = cpu_baseline(c, sample, threads)
@@ -317,7 +317,7 @@ def main():
             line["e2e"] = e2e
         if not args.no_cpu:
             threads = os.cpu_count() or 1
-            sample = min(P, args.cpu_sample_pairs or max(threads * 4, 8))
+            sample = min(P, args.cpu_sample_pairs or max(threads * 16, 64))
             hs = S.PairBatch(*[getattr(batch, f)[:sample].cpu() for f in ("src_des", "tgt_des", "src_xyz", "tgt_xyz", "T_gt", "perm", "inlier")])
             v, dt, Tc, _ = cpu_baseline(c, sample, threads, hs)
             same = bool(np.array_equal(Tc, T[:sample].cpu().numpy()))

@@ -38,6 +38,11 @@ def lib():
     return _lib
 
 
+def set_num_threads(n):
+    """threads used by the batched (OpenMP over pairs) entry points; returns the effective count"""
+    return int(lib().orc_set_num_threads(C.c_int(int(n))))
+
+
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None else None
 

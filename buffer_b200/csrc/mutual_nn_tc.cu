@@ -5,7 +5,7 @@
 //      significand bits, so |S~_ij - a_i.b_j| <= 2^-9 |a_i||b_j|; with eps = 2^-8 |a_i| max_j|b_j| every column whose exact
 //      score could be the row maximum satisfies  S~_ij + hn(b_j) >= max_j(S~_ij + hn(b_j)) - 2 eps.
 //   2. The epilogue (one thread per row, TMEM -> registers with tcgen05.ld) keeps the running approximate maximum and a
-//      short list of 8-column groups whose maximum was inside the 2-eps band when they streamed past (compacted when full).
+//      short list of 4-column groups whose maximum was inside the 2-eps band when they streamed past (compacted when full).
 //   3. Each thread re-evaluates its few candidates with the EXACT FP32 chain of the oracle (acc = hn(b); acc = fma(a_k, b_k,
 //      acc), k ascending) and publishes (key << 32 | ~index) with the same 64-bit RED.MAX as the FP32 kernel, so ties still
 //      go to the lowest index and the result is bit-identical by construction.  A list overflow (many near-duplicate
@@ -17,7 +17,7 @@
 //            (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier expect-tx)
 //   warp 1   TMEM allocator + MMA issuer: 2 halves x 4 tcgen05.mma (K = 4 x 8) per tile, tcgen05.commit -> ring slot free / accumulator full
 //   warps 2-9 epilogue (one thread per own row): tcgen05.ld 32 columns at a time, add hn(b_j) (shared-memory broadcast),
-//            FMNMX3 tree per 8-column group, predicated append of the groups inside the band
+//            FMNMX3 tree per 4-column group, predicated append of the groups inside the band
 #include "bfr_common.cuh"
 #include "bfr_kernels.h"
 #include <cuda.h>
@@ -33,7 +33,7 @@ constexpr int TC_D = 32;
 constexpr int TC_STAGES = 4;
 constexpr int TC_EPI_WARPS = 8;                 // one epilogue thread per own row
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_SUB = 8;                       // candidate granularity: 8-column groups
+constexpr int TC_SUB = 4;                       // candidate granularity: 4-column groups
 constexpr int TC_CAP = 24;                      // candidate groups kept per row
 constexpr int TC_MAX_TILES = 64;                // streamed tiles per CTA (hn cache = 8192 floats)
 
@@ -41,8 +41,7 @@ struct TcSmem {
     float a[TC_BM * TC_D];                      // 32 KB, SWIZZLE_128B K-major (one 128-byte atom per row); rows 128.. = second half
     float b[TC_STAGES][TC_BN * TC_D];           // 4 x 16 KB
     float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
-    float cv[TC_CAP][TC_BM];                    // candidate group maxima (approximate scores)  [slot][row]
-    int ci[TC_CAP][TC_BM];                      // first streamed column of the candidate group
+    uint2 cand[TC_CAP][TC_BM];                  // candidate groups [slot][row]: {approximate group maximum (float bits), first streamed column}
     float red[TC_THREADS / 32], red2[TC_THREADS / 32];
     uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -87,6 +86,13 @@ BFR_DEVINL void tmem_ld_wait(float (&v)[32])
                    "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]),
                    "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
                  :: "memory");
+}
+
+// append {value bits, column} at shared address `addr` and advance it by `stride` bytes iff val >= thr (no branch)
+BFR_DEVINL void append_if_ge(uint32_t& addr, float val, float thr, uint32_t col, uint32_t stride)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ge.f32 q, %1, %2;\n\t@q st.shared.v2.b32 [%0], {%3, %4};\n\t@q add.u32 %0, %0, %5;\n\t}"
+                 : "+r"(addr) : "f"(val), "f"(thr), "r"(__float_as_uint(val)), "r"(col), "r"(stride) : "memory");
 }
 
 // exact score of (own row, candidate row) — the oracle's chain.  COLDIR = the "own" side is the target set.
@@ -213,12 +219,15 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         const float own_hn = valid ? hn_own[(size_t)p * pad_own + row] : 0.0f;
         const float two_eps = 0.0078125f * sqrtf(fmaxf(-2.0f * own_hn, 0.0f) * fmaxf(str_max_sq, 0.0f)) + 1e-30f;   // 2 * 2^-8 |a| max|b|
         // Streamed norms (nearly) uniform -- L2-normalised descriptors, BUFFER's case: rank full tiles on the raw dot products
-        // (no hn add) and widen the band by the spread of hn; m_run then lives in "dot + hmax" units so both kinds of tile compare.
+        // (no hn add) and widen the band by the spread of hn; scores of hn-adjusted (partial) tiles are shifted by -hmax to match.
         const bool uniform = hn_spread <= 0.0009765625f * str_max_sq;   // CTA-uniform (the branch below contains warp-collective TMEM loads)
         const float band = uniform ? two_eps + hn_spread : two_eps;
-        float m_run = -INFINITY; int cnt = 0; bool overflow = false;
+        float m_run = -INFINITY; bool overflow = false;
+        const uint32_t cstride = (uint32_t)(sizeof(uint2) * TC_BM), cbase = smem_u32(&sm.cand[0][r]);
+        const uint32_t cguard = cbase + (uint32_t)(TC_CAP - 8) * cstride;   // room for the 8 groups of one chunk
+        uint32_t cptr = cbase;                                        // next free slot of this row's candidate list
 
-        // one 32-column chunk: add hn(b_j), 8-column group maxima, running maximum, predicated append of in-band groups
+        // one 32-column chunk: (add hn(b_j),) 4-column group maxima, running maximum, predicated append of in-band groups
         auto process = [&](float (&v)[32], int colbase, auto raw_tag) {
             constexpr bool RAW = decltype(raw_tag)::value;            // RAW: v stays the bare dot product, compared in "dot + hmax" units
             if (!RAW) {
@@ -229,27 +238,27 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                     unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
                 }
             }
-            float m8[4];
+            float mg[8];                                              // maxima of the eight 4-column groups, in raw dot-product units
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                m8[k] = fmaxf(max3(v[8 * k], v[8 * k + 1], v[8 * k + 2]), max3(v[8 * k + 3], v[8 * k + 4], max3(v[8 * k + 5], v[8 * k + 6], v[8 * k + 7])));
-                if (RAW) m8[k] += hmax;
+            for (int k = 0; k < 8; ++k) {
+                mg[k] = fmaxf(max3(v[4 * k], v[4 * k + 1], v[4 * k + 2]), v[4 * k + 3]);
+                if (!RAW) mg[k] -= hmax;                              // hn-adjusted tiles: shift so that both kinds of tile compare
             }
-            m_run = fmaxf(m_run, fmaxf(max3(m8[0], m8[1], m8[2]), m8[3]));
+            m_run = fmaxf(m_run, fmaxf(max3(max3(mg[0], mg[1], mg[2]), mg[3], mg[4]), max3(mg[5], mg[6], mg[7])));
             const float thr = m_run - band;
-            if (cnt > TC_CAP - 4) {                                   // rare: compact the list against the current band
+            if (cptr > cguard) {                                      // rare: compact the list against the current band
+                const int cnt = (int)((cptr - cbase) / cstride);
                 int n = 0;
                 for (int k = 0; k < cnt; ++k) {
-                    const float val = sm.cv[k][r];
-                    if (val >= thr) { sm.cv[n][r] = val; sm.ci[n][r] = sm.ci[k][r]; ++n; }
+                    const uint2 e = sm.cand[k][r];
+                    if (__uint_as_float(e.x) >= thr) { sm.cand[n][r] = e; ++n; }
                 }
-                cnt = n;
-                if (cnt > TC_CAP - 4) { overflow = true; cnt = 0; }
+                cptr = cbase + (uint32_t)n * cstride;
+                if (cptr > cguard) { overflow = true; cptr = cbase; }
             }
+            const uint32_t col0 = (uint32_t)(t_begin * TC_BN + colbase);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {                             // predicated append of the 8-column groups inside the band
-                if (m8[k] >= thr) { sm.cv[cnt][r] = m8[k]; sm.ci[cnt][r] = t_begin * TC_BN + colbase + 8 * k; ++cnt; }
-            }
+            for (int k = 0; k < 8; ++k) append_if_ge(cptr, mg[k], thr, col0 + 4u * k, cstride);   // groups inside the band
         };
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int it = 0; it < ntiles; ++it) {
@@ -285,46 +294,82 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         tq2 = clock64();
 #endif
         // ---- exact FP32 re-check of the surviving groups (or of the whole row after an overflow) ---------------------------
-        if (valid) {
-            float4 own[8];
-            const float4* o4 = reinterpret_cast<const float4*>(x_own + (size_t)(oo + row) * TC_D);
+        // One lane = one row, but the candidate rows are fetched cooperatively: 8 lanes read the 8 float4 of one 128-byte row
+        // (coalesced, 4 rows per warp-wide load) and transpose through an XOR-swizzled per-warp staging area carved out of the
+        // now idle TMA ring, so that the L1 sees 4 wavefronts per load instruction instead of 32.
+        {
+            float4* stage = reinterpret_cast<float4*>(&sm.b[0][0]) + (warp - 2) * 512;     // 2 buffers x (32 rows x 8 float4)
+            const int sub = lane >> 3, chunk = lane & 7;
+            // gather 32 rows (one per lane, row index `want`, -1 = none) of `base` into registers, 4 rows per instruction
+            auto fetch = [&](const float* __restrict__ base, int want, float4 (&reg)[8]) {
 #pragma unroll
-            for (int k4 = 0; k4 < 8; ++k4) own[k4] = __ldg(o4 + k4);
-            float best = -INFINITY; int best_j = 0x7fffffff;
+                for (int s8 = 0; s8 < 8; ++s8) {
+                    const int rid = 4 * s8 + sub;
+                    const int jr = __shfl_sync(0xffffffffu, want, rid);
+                    reg[s8] = (jr >= 0) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)jr * TC_D) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            auto put = [&](int buf, const float4 (&reg)[8]) {
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) { const int rid = 4 * s8 + sub; stage[buf * 256 + rid * 8 + (chunk ^ (rid & 7))] = reg[s8]; }
+            };
+            auto get = [&](int buf, float4 (&rowv)[8]) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) rowv[c] = stage[buf * 256 + lane * 8 + (c ^ (lane & 7))];
+            };
+            float4 own[8], reg[8];
+            __syncwarp();
+            fetch(x_own + (size_t)oo * TC_D, valid ? row : -1, reg);
+            put(0, reg);
+            __syncwarp();
+            get(0, own);
+            __syncwarp();
             const float thr = m_run - band;
             const int j_end = min(N, t_end * TC_BN);
-            if (!overflow) {
-                int n = 0;                                            // compact the survivors so that the warp's lanes stay aligned
-                for (int k = 0; k < cnt; ++k)
-                    if (sm.cv[k][r] >= thr) { sm.ci[n][r] = sm.ci[k][r]; ++n; }
-#ifdef TC_TIMING
-                { long long tz = clock64(); int nmx = __reduce_max_sync(0xffffffffu, n), cmx = __reduce_max_sync(0xffffffffu, cnt), nsum = __reduce_add_sync(0xffffffffu, n);
-                  if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && warp == 2) printf("verify: own+compact %lld cycles, cnt max %d, n max %d, n sum %d\n", tz - tq2, cmx, nmx, nsum); }
-#endif
-                for (int k = 0; k < n; ++k) {
-                    const int j0 = sm.ci[k][r];
-#pragma unroll 1
-                    for (int jb = j0; jb < min(j0 + TC_SUB, j_end); jb += 4) {
-                        float e[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {                 // 4 independent exact chains in flight (padding rows re-read column jb)
-                            const int j = (jb + u < j_end) ? jb + u : jb;
-                            e[u] = exact_score<COLDIR>(own, own_hn, x_str + (size_t)(os + j) * TC_D, hn_str_p[j]);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const int j = jb + u;
-                            if (j < j_end && (e[u] > best || (e[u] == best && j < best_j))) { best = e[u]; best_j = j; }
-                        }
-                    }
+            float best = -INFINITY; int best_j = 0x7fffffff;
+            int n = 0;                                                // compact the survivors so that the warp's lanes stay aligned
+            const int cnt = (int)((cptr - cbase) / cstride);
+            if (valid && !overflow)
+                for (int k = 0; k < cnt; ++k) {
+                    const uint2 e = sm.cand[k][r];
+                    if (__uint_as_float(e.x) >= thr) { sm.cand[n][r] = e; ++n; }
                 }
-            } else {
+            const int nmax = __reduce_max_sync(0xffffffffu, n);
+            const float* xs = x_str + (size_t)os * TC_D;
+            auto column = [&](int k, int u) {                         // streamed column this lane evaluates in sub-round (k, u), or -1
+                if (k >= n) return -1;
+                const int j = (int)sm.cand[k][r].y + u;
+                return j < j_end ? j : -1;
+            };
+            const int rounds = nmax * TC_SUB;
+            if (rounds > 0) { fetch(xs, column(0, 0), reg); put(0, reg); }
+            for (int it = 0; it < rounds; ++it) {
+                const int j = column(it / TC_SUB, it % TC_SUB);
+                const bool more = it + 1 < rounds;
+                if (more) fetch(xs, column((it + 1) / TC_SUB, (it + 1) % TC_SUB), reg);     // next sub-round's loads in flight
+                __syncwarp();
+                if (j >= 0) {
+                    float4 c[8];
+                    get(it & 1, c);
+                    const float cand_hn = sm.hn[j - t_begin * TC_BN];
+                    float acc = COLDIR ? own_hn : cand_hn;
+#pragma unroll
+                    for (int k4 = 0; k4 < 8; ++k4) {
+                        acc = __fmaf_rn(own[k4].x, c[k4].x, acc); acc = __fmaf_rn(own[k4].y, c[k4].y, acc);
+                        acc = __fmaf_rn(own[k4].z, c[k4].z, acc); acc = __fmaf_rn(own[k4].w, c[k4].w, acc);
+                    }
+                    const float e = COLDIR ? __fadd_rn(acc, cand_hn) : acc;
+                    if (e > best || (e == best && j < best_j)) { best = e; best_j = j; }
+                }
+                if (more) put((it + 1) & 1, reg);
+            }
+            if (valid && overflow) {                                  // pathological row (many near-duplicates): exact scan
                 for (int j = t_begin * TC_BN; j < j_end; ++j) {
-                    const float e = exact_score<COLDIR>(own, own_hn, x_str + (size_t)(os + j) * TC_D, hn_str_p[j]);
+                    const float e = exact_score<COLDIR>(own, own_hn, xs + (size_t)j * TC_D, hn_str_p[j]);
                     if (e > best) { best = e; best_j = j; }
                 }
             }
-            if (best_j != 0x7fffffff)
+            if (valid && best_j != 0x7fffffff)
                 red_max_u64(out_packed + (size_t)p * pad_own + row, pack_best(float_key(best), (uint32_t)best_j));
         }
     }

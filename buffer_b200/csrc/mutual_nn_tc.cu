@@ -88,13 +88,6 @@ BFR_DEVINL void tmem_ld_wait(float (&v)[32])
                  :: "memory");
 }
 
-// append {value bits, column} at shared address `addr` and advance it by `stride` bytes iff val >= thr (no branch)
-BFR_DEVINL void append_if_ge(uint32_t& addr, float val, float thr, uint32_t col, uint32_t stride)
-{
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ge.f32 q, %1, %2;\n\t@q st.shared.v2.b32 [%0], {%3, %4};\n\t@q add.u32 %0, %0, %5;\n\t}"
-                 : "+r"(addr) : "f"(val), "f"(thr), "r"(__float_as_uint(val)), "r"(col), "r"(stride) : "memory");
-}
-
 // exact score of (own row, candidate row) — the oracle's chain.  COLDIR = the "own" side is the target set.
 template <bool COLDIR>
 BFR_DEVINL float exact_score(const float4 (&own)[8], float own_hn, const float* __restrict__ cand_row, float cand_hn)
@@ -222,10 +215,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         // (no hn add) and widen the band by the spread of hn; scores of hn-adjusted (partial) tiles are shifted by -hmax to match.
         const bool uniform = hn_spread <= 0.0009765625f * str_max_sq;   // CTA-uniform (the branch below contains warp-collective TMEM loads)
         const float band = uniform ? two_eps + hn_spread : two_eps;
-        float m_run = -INFINITY; bool overflow = false;
-        const uint32_t cstride = (uint32_t)(sizeof(uint2) * TC_BM), cbase = smem_u32(&sm.cand[0][r]);
-        const uint32_t cguard = cbase + (uint32_t)(TC_CAP - 8) * cstride;   // room for the 8 groups of one chunk
-        uint32_t cptr = cbase;                                        // next free slot of this row's candidate list
+        float m_run = -INFINITY; int cnt = 0; bool overflow = false;
 
         // one 32-column chunk: (add hn(b_j),) 4-column group maxima, running maximum, predicated append of in-band groups
         auto process = [&](float (&v)[32], int colbase, auto raw_tag) {
@@ -246,19 +236,19 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             }
             m_run = fmaxf(m_run, fmaxf(max3(max3(mg[0], mg[1], mg[2]), mg[3], mg[4]), max3(mg[5], mg[6], mg[7])));
             const float thr = m_run - band;
-            if (cptr > cguard) {                                      // rare: compact the list against the current band
-                const int cnt = (int)((cptr - cbase) / cstride);
+            if (cnt > TC_CAP - 8) {                                   // rare: compact the list against the current band
                 int n = 0;
                 for (int k = 0; k < cnt; ++k) {
                     const uint2 e = sm.cand[k][r];
                     if (__uint_as_float(e.x) >= thr) { sm.cand[n][r] = e; ++n; }
                 }
-                cptr = cbase + (uint32_t)n * cstride;
-                if (cptr > cguard) { overflow = true; cptr = cbase; }
+                cnt = n;
+                if (cnt > TC_CAP - 8) { overflow = true; cnt = 0; }
             }
-            const uint32_t col0 = (uint32_t)(t_begin * TC_BN + colbase);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) append_if_ge(cptr, mg[k], thr, col0 + 4u * k, cstride);   // groups inside the band
+            for (int k = 0; k < 8; ++k) {                             // predicated append of the groups inside the band (one 64-bit store each)
+                if (mg[k] >= thr) { sm.cand[cnt][r] = make_uint2(__float_as_uint(mg[k]), (uint32_t)(t_begin * TC_BN + colbase + 4 * k)); ++cnt; }
+            }
         };
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
         for (int it = 0; it < ntiles; ++it) {
@@ -328,7 +318,6 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             const int j_end = min(N, t_end * TC_BN);
             float best = -INFINITY; int best_j = 0x7fffffff;
             int n = 0;                                                // compact the survivors so that the warp's lanes stay aligned
-            const int cnt = (int)((cptr - cbase) / cstride);
             if (valid && !overflow)
                 for (int k = 0; k < cnt; ++k) {
                     const uint2 e = sm.cand[k][r];

@@ -58,6 +58,31 @@ def test_mutual_nn_unnormalised_and_splits(oracle, backend, algo):
         assert np.array_equal(r["nn_t"].cpu().numpy(), nn_t), splits
 
 
+def test_mutual_nn_adversarial_inputs(oracle, backend, algo):
+    """near-duplicate floods (candidate-list overflow -> exact scan), exact duplicates (ties -> lowest index), zero rows,
+    huge / tiny norms, and a target set wide enough to need column splits in the tensor-core kernel (N > 8192)"""
+    g = torch.Generator().manual_seed(77)
+    nrm = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    cases = []
+    base = nrm(torch.randn(1, 32, generator=g))
+    flood = nrm(base + 1e-4 * torch.randn(600, 32, generator=g))            # 600 targets inside everybody's 2-eps band
+    cases.append((nrm(base + 1e-3 * torch.randn(300, 32, generator=g)), torch.cat([flood, nrm(torch.randn(400, 32, generator=g))])))
+    dup_t = nrm(torch.randn(50, 32, generator=g)).repeat(20, 1)               # every target row 20 times: exact ties
+    cases.append((nrm(torch.randn(700, 32, generator=g)), dup_t))
+    z = nrm(torch.randn(500, 32, generator=g)); z[::7] = 0.0                  # zero descriptors
+    cases.append((z, nrm(torch.randn(450, 32, generator=g))))
+    cases.append((1e3 * torch.randn(400, 32, generator=g), 1e3 * torch.randn(500, 32, generator=g)))
+    cases.append((1e-3 * torch.randn(400, 32, generator=g), 1e-3 * torch.randn(500, 32, generator=g) * torch.rand(500, 1, generator=g)))
+    cases.append((nrm(torch.randn(300, 32, generator=g)), nrm(torch.randn(9000, 32, generator=g))))
+    cases.append((nrm(torch.randn(9000, 32, generator=g)), nrm(torch.randn(300, 32, generator=g))))
+    for src, tgt in cases:
+        nn_s, nn_t, ds, dt = oracle.mutual_nn(src.numpy(), tgt.numpy(), want_dist=True)
+        r = backend.mutual_matching_device(src.to(DEV), tgt.to(DEV), want_dist=True)
+        assert np.array_equal(r["nn_s"].cpu().numpy(), nn_s)
+        assert np.array_equal(r["nn_t"].cpu().numpy(), nn_t)
+        assert np.array_equal(r["dist_s"].cpu().numpy(), ds) and np.array_equal(r["dist_t"].cpu().numpy(), dt)
+
+
 def test_mutual_matching_batched_varlen(oracle, backend, algo):
     sizes = [(300, 200), (1, 7), (1025, 513), (64, 640), (5, 5)]
     g = torch.Generator().manual_seed(11)

@@ -6,6 +6,11 @@ rows = list(csv.reader(open(sys.argv[1])))
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 hdr = rows[1]; ci = {h: i for i, h in enumerate(hdr)}
 body = rows[2:]
+for i, r in enumerate(body):            # several kernels in one report: keep the first section only
+    if r and r[0] == "Kernel Name":
+        body = body[:i]
+        break
+body = [r for r in body if len(r) == len(hdr)]
 tot = sum(int(r[ci["# Samples"]] or 0) for r in body)
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 print("total samples", tot)

@@ -303,6 +303,48 @@ def post_refinement(initial_trans, src_keypts, tgt_keypts, weights=None, dataset
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# "next" rows
+# ---------------------------------------------------------------------------------------------------------------
+def get_matching_indices_device(source, target, relt_pose, search_voxel_size):
+    """no-sync variant -> (match_inds [N,2] int64 padded, count [1] int32, nn [N] int64, dist [N] float32)"""
+    source = _f32c(source, "source"); target = _f32c(target, "target"); T = _f32c(relt_pose, "relt_pose").reshape(16)
+    dev = source.device
+    N, M = source.shape[0], target.shape[0]
+    pairs = torch.empty(max(N, 1), 2, dtype=torch.int64, device=dev); count = torch.zeros(1, dtype=torch.int32, device=dev)
+    nn = torch.empty(max(N, 1), dtype=torch.int64, device=dev); dist = torch.empty(max(N, 1), dtype=torch.float32, device=dev)
+    L = _lib.lib()
+    ws = _ws(L.bfr_get_matching_indices_workspace_bytes(N), dev, "knn3")
+    _lib.check(L.bfr_get_matching_indices(source.data_ptr(), N, target.data_ptr(), M, T.data_ptr(), float(search_voxel_size), pairs.data_ptr(),
+                                          count.data_ptr(), nn.data_ptr(), dist.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bfr_get_matching_indices")
+    return pairs, count, nn[:N], dist[:N]
+
+
+def get_matching_indices(source, target, relt_pose, search_voxel_size):
+    """Drop-in for buffer.get_matching_indices (models/BUFFER.py:361-380): -> match_inds [C,2] int64 CUDA tensor"""
+    pairs, count, _, _ = get_matching_indices_device(source, target, relt_pose, search_voxel_size)
+    return pairs[: int(count.item())]
+
+
+def svd(x):
+    """torch_batch_svd.svd drop-in (utils/common.py:10,715): x [B,3,3] CUDA -> (u [B,3,3], s [B,3] descending, v [B,3,3])"""
+    x = _f32c(x, "x")
+    if x.dim() != 3 or x.shape[1:] != (3, 3):
+        raise RuntimeError("buffer_b200.svd: expected [B,3,3]")
+    B = x.shape[0]
+    u = torch.empty(B, 3, 3, dtype=torch.float32, device=x.device); s = torch.empty(B, 3, dtype=torch.float32, device=x.device); v = torch.empty_like(u)
+    _lib.check(_lib.lib().bfr_svd3_batched(x.data_ptr(), B, u.data_ptr(), s.data_ptr(), v.data_ptr(), _stream()), "bfr_svd3_batched")
+    return u, s, v
+
+
+def lrf_vote(ind, ss_R, tt_R, ss_kpts, tt_kpts, azi_n=20, inlier_th=1 / 3):
+    """lines 294-311 of models/BUFFER.py in one call, everything stays on the device (no .cpu() at :311):
+    -> R [A,3,3], t [A,3], inlier_num [A] int32, best_ind [1] int64, inlier_mask [A] bool"""
+    R, t = lrf_hypotheses(ind, ss_R, tt_R, ss_kpts, tt_kpts, azi_n)
+    counts, best, mask = score_hypotheses(R, t, ss_kpts, tt_kpts, inlier_threshold(_f32c(ss_kpts, "ss_kpts"), azi_n, inlier_th))
+    return R, t, counts, best, mask
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # whole back end
 # ---------------------------------------------------------------------------------------------------------------
 def register_batched(src_des, src_xyz, src_off, tgt_des, tgt_xyz, tgt_off, max_M, max_N, hypotheses=50000, dist_th=0.10, similar_th=0.8,

@@ -229,6 +229,27 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
     return BFR_OK;
 }
 
+size_t bfr_get_matching_indices_workspace_bytes(int N) { return knn3_workspace_bytes(N); }
+
+int bfr_get_matching_indices(const float* source, int N, const float* target, int M, const float* relt_pose, float search_voxel_size,
+                             int64_t* match_inds, int32_t* count, int64_t* nn, float* dist, void* ws, size_t ws_bytes, void* stream)
+{
+    if (!match_inds || !count || !ws || !relt_pose) return BFR_E_NULL;
+    if (N < 0 || M < 0) return BFR_E_SIZE;
+    if (N > 0 && !source) return BFR_E_NULL;
+    if (M > 0 && !target) return BFR_E_NULL;
+    if (ws_bytes < knn3_workspace_bytes(N)) return BFR_E_WORKSPACE;
+    return cu(get_matching_indices_launch(source, N, target, M, relt_pose, search_voxel_size, match_inds, count, nn, dist, ws, st(stream)));
+}
+
+int bfr_svd3_batched(const float* x, int B, float* u, float* s, float* v, void* stream)
+{
+    if (B == 0) return BFR_OK;
+    if (!x || !u || !s || !v) return BFR_E_NULL;
+    if (B < 0) return BFR_E_SIZE;
+    return cu(svd3_launch(x, B, u, s, v, st(stream)));
+}
+
 int bfr_config_set(int key, int value)
 {
     if (key == BFR_CFG_K1_ALGO) { if (value != 0 && value != 1) return BFR_E_SIZE; k1_set_algo(value); return BFR_OK; }

@@ -40,4 +40,10 @@ cudaError_t rigid_transform_launch(const float* A, const float* B, const float* 
 cudaError_t post_refinement_launch(const float* T0, const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, float thr, int max_iter,
                                    float* Tout, int32_t* iters_out, int32_t* inliers_out, cudaStream_t stream);
 
+// "next" rows (extras.cu)
+size_t knn3_workspace_bytes(int N);
+cudaError_t get_matching_indices_launch(const float* source, int N, const float* target, int M, const float* T, float voxel,
+                                        int64_t* pairs, int32_t* count, int64_t* nn_out, float* dist_out, void* ws, cudaStream_t stream);
+cudaError_t svd3_launch(const float* x, int B, float* u, float* s, float* v, cudaStream_t stream);
+
 }  // namespace bfr

@@ -4,6 +4,7 @@
 
   B.buffer.mutual_matching   -> K1 (models/BUFFER.py:335-359)
   B.buffer.post_refinement   -> K4 loop (models/BUFFER.py:382-418), threshold chosen from self.config.data.dataset
+  B.buffer.get_matching_indices -> 3-D nearest neighbour + voxel filter (models/BUFFER.py:361-380)
   B.rigid_transform_3d       -> K4 weighted Kabsch (models/BUFFER.py:424-464)
   B.KNN                      -> K1-backed k=1 nearest neighbour for 32-d descriptors (models/BUFFER.py:347,352)
   B.o3d.pipelines.registration.registration_ransac_based_on_correspondence (+ the estimator / checker / criteria
@@ -71,8 +72,12 @@ def install(B, replace_open3d=True):
     def post_refinement(self, initial_trans, src_keypts, tgt_keypts, weights=None):
         return backend.post_refinement(initial_trans, src_keypts, tgt_keypts, weights, dataset=self.config.data.dataset)
 
+    def get_matching_indices(self, source, target, relt_pose, search_voxel_size):
+        return backend.get_matching_indices(source, target, relt_pose, search_voxel_size)
+
     B.buffer.mutual_matching = mutual_matching
     B.buffer.post_refinement = post_refinement
+    B.buffer.get_matching_indices = get_matching_indices
     B.rigid_transform_3d = backend.rigid_transform_3d
     B.KNN = _KNN1
     if replace_open3d:

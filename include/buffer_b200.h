@@ -121,6 +121,19 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
                               float dist_th, float similar_th, float refine_thr, int refine_iters, int ransac_splits,
                               float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- "next" rows ------------------------------------------------------------------------------------
+ * bfr_get_matching_indices replaces buffer.get_matching_indices (models/BUFFER.py:361-380; twins ThreeDMatch/dataset.py:14-22,
+ * ThreeDMatch/trainer.py:38-54): source [N][3] is transformed by relt_pose (DEVICE pointer to a row-major 4x4), every
+ * transformed point gets its nearest target [M][3] point, and the pairs with distance < search_voxel_size are written in
+ * ascending source order to match_inds [N][2] (int64, like the reference) with their number in count[0]; nn [N] / dist [N]
+ * (optional) receive every source point's nearest index and distance.
+ * bfr_svd3_batched is the torch_batch_svd.svd contract of cal_Z_axis (utils/common.py:715): x [B][9] -> u [B][9], s [B][3]
+ * (descending), v [B][9], x = u diag(s) v^T. */
+size_t bfr_get_matching_indices_workspace_bytes(int N);
+int bfr_get_matching_indices(const float* source, int N, const float* target, int M, const float* relt_pose, float search_voxel_size,
+                             int64_t* match_inds, int32_t* count, int64_t* nn, float* dist, void* ws, size_t ws_bytes, void* stream);
+int bfr_svd3_batched(const float* x, int B, float* u, float* s, float* v, void* stream);
+
 /* ---- measurement aids (used by bench.py only) ---------------------------------------------------------------------
  * bfr_fp32_probe: a pure FFMA2 stream on `grid` CTAs of 256 threads, executing grid*256*iters*256 FMAs (2 flop each);
  * scratch: device floats, >= grid*256 + 128, first 128 initialised by the caller to finite values.  The measured rate

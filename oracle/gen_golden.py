@@ -111,6 +111,23 @@ def main():
     np.savez(os.path.join(OUT, "ransac.npz"), ss=ss, tt=tt, samples=samples, seed=np.uint64(seed), pair_id=np.uint32(pair_id), H=np.int64(H),
              dist_th=np.float32(0.10), similar_th=np.float32(0.8), T_best=T_best, best_count=np.int64(best_cnt), best_h=np.int64(best_h), counts=counts,
              T_gt=b.T_gt[0].numpy())
+    # ---- "next" rows: get_matching_indices (numpy twin ThreeDMatch/dataset.py:14-22) and cal_Z_axis' SVD ---------------------
+    import ThreeDMatch.dataset as TD
+    import utils.common as UC
+    gm_src = (torch.rand(700, 3, generator=g) * 2).numpy()
+    Tg = b.T_gt[0].numpy()
+    moved = gm_src @ Tg[:3, :3].T + Tg[:3, 3]
+    gm_tgt = (moved + 0.02 * torch.randn(700, 3, generator=g).numpy())[torch.randperm(700, generator=g).numpy()][:610].astype(np.float32)
+    gm = TD.get_matching_indices(gm_src, gm_tgt, Tg, 0.05)
+    local = torch.randn(40, 64, 3, generator=g) * torch.tensor([1.0, 0.6, 0.15])
+    local = local @ torch.from_numpy(rot(g, 40)).transpose(-1, -2)
+    refp = torch.randn(40, 3, generator=g)
+    z_axis = UC.cal_Z_axis(local, ref_point=refp).numpy()                      # uses the torch_batch_svd stub = torch.svd
+    cov = torch.matmul(local.transpose(-1, -2), local)
+    u_, s_, v_ = torch.svd(cov)
+    np.savez(os.path.join(OUT, "next_rows.npz"), gm_src=gm_src, gm_tgt=gm_tgt, gm_T=Tg, gm_voxel=np.float32(0.05), gm_pairs=gm,
+             local=local.numpy(), ref_point=refp.numpy(), z_axis=z_axis, cov=cov.numpy(), svd_u=u_.numpy(), svd_s=s_.numpy(), svd_v=v_.numpy())
+
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -174,6 +174,25 @@ def post_refinement(T0, corr, thr, max_iter=20):
     return T.reshape(4, 4), it.value, li.value
 
 
+def get_matching_indices(source, target, relt_pose, search_voxel_size, want_nn=False):
+    """oracle of buffer.get_matching_indices (models/BUFFER.py:361-380) -> match_inds [C,2] int64 (, nn [N], dist [N])"""
+    source = _f32(source); target = _f32(target); T = _f32(relt_pose).reshape(16)
+    N, M = source.shape[0], target.shape[0]
+    pairs = np.zeros((max(N, 1), 2), np.int64); nn = np.zeros(N, np.int64); dist = np.zeros(N, np.float32)
+    lib().orc_get_matching_indices.restype = C.c_int
+    c = lib().orc_get_matching_indices(_p(source), C.c_int(N), _p(target), C.c_int(M), _p(T), C.c_float(search_voxel_size), _p(pairs), _p(nn), _p(dist))
+    return (pairs[:c].copy(), nn, dist) if want_nn else pairs[:c].copy()
+
+
+def svd3(x):
+    """batched 3x3 SVD (torch_batch_svd contract, utils/common.py:715): x [B,3,3] -> u [B,3,3], s [B,3] descending, v [B,3,3]"""
+    x = _f32(x).reshape(-1, 9); B = x.shape[0]
+    u = np.zeros((B, 9), np.float32); s = np.zeros((B, 3), np.float32); v = np.zeros((B, 9), np.float32)
+    for b in range(B):
+        lib().orc_svd3(_p(x[b]), _p(u[b]), _p(s[b]), _p(v[b]))
+    return u.reshape(B, 3, 3), s, v.reshape(B, 3, 3)
+
+
 def register_batched(src_des, src_xyz, src_off, tgt_des, tgt_xyz, tgt_off, H, seed, pair_id_base, dist_th, similar_th,
                      refine_thr, refine_iters=20):
     """whole back end on the CPU for a batch of pairs (OpenMP over pairs) -> T [P,4,4], n_mutual [P], n_inliers [P]"""

@@ -220,6 +220,53 @@ def test_post_refinement_bit_exact(oracle, backend):
         assert it_o >= 1 and inl_o > 300
 
 
+@pytest.mark.parametrize("N,M", [(0, 5), (1, 1), (300, 257), (4097, 3000)])
+def test_get_matching_indices_bit_exact(oracle, backend, N, M):
+    g = torch.Generator().manual_seed(N * 31 + M)
+    src = torch.rand(N, 3, generator=g) * 3
+    T = torch.eye(4); T[:3, :3] = S.quat_to_rot(torch.randn(1, 4, generator=g))[0]; T[:3, 3] = torch.randn(3, generator=g)
+    tgt = (torch.rand(M, 3, generator=g) * 3) @ T[:3, :3].T + T[:3, 3]
+    k = min(N, M) // 2
+    if k:
+        tgt[:k] = src[:k] @ T[:3, :3].T + T[:3, 3] + 0.01 * torch.randn(k, 3, generator=g)
+        tgt[1] = tgt[0]                                              # exact tie -> lowest index
+    pairs_o, nn_o, dist_o = oracle.get_matching_indices(src.numpy(), tgt.numpy(), T.numpy(), 0.05, want_nn=True)
+    pairs, count, nn, dist = backend.get_matching_indices_device(src.to(DEV), tgt.to(DEV), T.to(DEV), 0.05)
+    assert int(count.item()) == len(pairs_o)
+    assert np.array_equal(pairs[: len(pairs_o)].cpu().numpy(), pairs_o)
+    assert np.array_equal(nn.cpu().numpy(), nn_o) and np.array_equal(dist.cpu().numpy(), dist_o)
+    m = backend.get_matching_indices(src.to(DEV), tgt.to(DEV), T.to(DEV), 0.05)
+    assert m.is_cuda and m.dtype == torch.int64 and np.array_equal(m.cpu().numpy(), pairs_o)
+
+
+def test_batched_svd3_bit_exact(oracle, backend):
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1000, 3, 3, generator=g)
+    x[:100] = x[:100] @ x[:100].transpose(-1, -2)                   # covariance-like (cal_Z_axis' input)
+    x[100] = 0; x[101] = torch.outer(torch.tensor([1., 2., 3.]), torch.tensor([3., 2., 1.])); x[102, :, 2] = x[102, :, 0]
+    x[103] = torch.eye(3); x[104] = torch.diag(torch.tensor([3., 3., 1.]))
+    uo, so, vo = oracle.svd3(x.numpy())
+    u, s, v = backend.svd(x.to(DEV))
+    assert np.array_equal(u.cpu().numpy(), uo) and np.array_equal(s.cpu().numpy(), so) and np.array_equal(v.cpu().numpy(), vo)
+    rec = u @ torch.diag_embed(s) @ v.transpose(-1, -2)
+    assert float((rec.cpu() - x).abs().max()) < 2e-5 and bool((s[:, :-1] >= s[:, 1:]).all())
+    eye = torch.eye(3, device=DEV)
+    assert float((u.transpose(-1, -2) @ u - eye).abs().max()) < 1e-5 and float((v.transpose(-1, -2) @ v - eye).abs().max()) < 1e-5
+    ref = torch.linalg.svdvals(x.double())
+    assert float((s.cpu().double() - ref).abs().max()) < 1e-5 * float(ref.max())
+
+
+def test_lrf_vote_matches_separate_calls(backend):
+    A = 300
+    g = torch.Generator().manual_seed(4)
+    ss_R = S.quat_to_rot(torch.randn(A, 4, generator=g)).to(DEV); tt_R = S.quat_to_rot(torch.randn(A, 4, generator=g)).to(DEV)
+    ss = (torch.rand(A, 3, generator=g) * 3).to(DEV); tt = (torch.rand(A, 3, generator=g) * 3).to(DEV); ind = (torch.rand(A, generator=g) * 20).to(DEV)
+    R, t, counts, best, mask = backend.lrf_vote(ind, ss_R, tt_R, ss, tt)
+    R2, t2 = backend.lrf_hypotheses(ind, ss_R, tt_R, ss, tt)
+    c2, b2, m2 = backend.score_hypotheses(R2, t2, ss, tt, backend.inlier_threshold(ss))
+    assert torch.equal(R, R2) and torch.equal(counts, c2) and torch.equal(best, b2) and torch.equal(mask, m2)
+
+
 def test_register_pipeline_matches_oracle_and_recovers_pose(oracle, backend, algo):
     P, N, H = 6, 1200, 8000
     b = _pairs(P, N, cfg_id=17)

@@ -101,6 +101,23 @@ def test_ransac_equals_reference_semantics(oracle):
     assert ok == 1.0
 
 
+def test_next_rows_equal_reference(oracle):
+    g = load("next_rows")
+    pairs = oracle.get_matching_indices(g["gm_src"], g["gm_tgt"], g["gm_T"], float(g["gm_voxel"]))
+    assert pairs.dtype == np.int64 and np.array_equal(pairs, g["gm_pairs"])          # ThreeDMatch/dataset.py:14-22
+    u, s, v = oracle.svd3(g["cov"])                                                   # torch_batch_svd contract, utils/common.py:715
+    assert np.abs(s - g["svd_s"]).max() < 2e-4 * g["svd_s"].max() and np.all(np.diff(s, axis=1) <= 0)
+    rec = np.einsum("bij,bj,bkj->bik", u, s, v)
+    assert np.abs(rec - g["cov"]).max() < 1e-4 * np.abs(g["cov"]).max()
+    for a, b_ in ((u, g["svd_u"]), (v, g["svd_v"])):                                  # singular vectors agree up to sign
+        assert np.abs(np.abs(np.einsum("bik,bik->bk", a, b_)) - 1).max() < 1e-4
+    # cal_Z_axis = u[:, :, -1] with the reference's sign disambiguation
+    z = u[:, :, -1]
+    flip = (np.sum(-z * g["ref_point"], axis=1) < 0)[:, None]
+    z = np.where(flip, -z, z)
+    assert np.abs(z - g["z_axis"]).max() < 1e-4
+
+
 def test_oracle_properties(oracle):
     """SE(3) recovery from noiseless inliers, invariance to outlier positions, SO(3) membership, K < 3 -> identity"""
     b = S.make_pairs(2, 600, cfg_id=55, sigma=0.0)

@@ -309,3 +309,63 @@ def test_full_size_properties(backend, algo):
     R = T[:, :3, :3].double().cpu()
     assert float((R @ R.transpose(-1, -2) - torch.eye(3, dtype=torch.float64)).abs().max()) < 1e-5
     assert torch.allclose(torch.det(R), torch.ones(P, dtype=torch.float64), atol=1e-5)
+
+
+def _subset_check(oracle, backend, src, tgt, rows=150):
+    """exactness at sizes the oracle cannot scan fully: nearest neighbours of random row subsets against the oracle"""
+    g = torch.Generator().manual_seed(3)
+    r = backend.mutual_matching_device(src, tgt)
+    si = torch.randperm(src.shape[0], generator=g)[:rows]; ti = torch.randperm(tgt.shape[0], generator=g)[:rows]
+    nn_s, _ = oracle.mutual_nn(src[si.to(src.device)].cpu().numpy(), tgt.cpu().numpy())
+    _, nn_t = oracle.mutual_nn(src.cpu().numpy(), tgt[ti.to(tgt.device)].cpu().numpy())
+    assert np.array_equal(r["nn_s"][si.to(src.device)].cpu().numpy(), nn_s)
+    assert np.array_equal(r["nn_t"][ti.to(tgt.device)].cpu().numpy(), nn_t)
+    return r
+
+
+def test_config3_low_overlap_many_hypotheses(oracle, backend):
+    """BASELINE config 3: ~95 % outliers, 500k hypotheses per pair"""
+    c = S.CONFIGS[3]
+    b = S.make_pairs(2, 5000, first_pair=0, **{k: v for k, v in c["gen"].items() if k != "num_kpts"}).to(DEV)
+    T, nm, ni = backend.register_uniform(b.src_des, b.src_xyz, b.tgt_des, b.tgt_xyz, hypotheses=c["hypotheses"], seed=5)
+    recall, rte, rre = S.registration_recall(T.cpu(), b.T_gt.cpu())
+    assert recall == 1.0 and float(rte.max()) < 0.02
+    assert torch.equal(ni.cpu(), b.inlier.sum(-1).int().cpu()) or int((ni.cpu() - b.inlier.sum(-1).int().cpu()).abs().max()) <= 3
+    # exactness of the RANSAC winner on one pair against the oracle (H = 500k takes ~1 s on the CPU)
+    s, t = oracle.mutual_matching(b.src_des[0].cpu().numpy(), b.tgt_des[0].cpu().numpy())
+    corr = oracle.gather_corr(b.src_xyz[0].cpu().numpy(), b.tgt_xyz[0].cpu().numpy(), s, t)
+    best = oracle.ransac(corr, 5, 0, c["hypotheses"], c["dist_th"], c["similar_th"])
+    assert (best >> 32) == int(ni[0])
+
+
+def test_config4_kitti_scale(oracle, backend):
+    """BASELINE config 4: 20k keypoints, 0.6 m inlier threshold, KITTI-sized scene"""
+    c = S.CONFIGS[4]
+    b = S.make_pairs(2, 20000, first_pair=0, **{k: v for k, v in c["gen"].items() if k != "num_kpts"}).to(DEV)
+    _subset_check(oracle, backend, b.src_des[0], b.tgt_des[0])
+    T, nm, ni = backend.register_uniform(b.src_des, b.src_xyz, b.tgt_des, b.tgt_xyz, hypotheses=c["hypotheses"], dist_th=c["dist_th"],
+                                         similar_th=c["similar_th"], refine_thr=c["refine_thr"], seed=2)
+    recall, rte, rre = S.registration_recall(T.cpu(), b.T_gt.cpu(), rte_thresh=0.3, rre_thresh_deg=1.0)   # KITTI/test.py:66-67
+    assert recall == 1.0 and int(nm.min()) == 20000
+
+
+def test_config5_huge_pair_split_by_hypothesis(oracle, backend):
+    """BASELINE config 5: one 100k x 100k pair; hypotheses evaluated in 4 slices (as 4 ranks would) and max-merged"""
+    b = S.make_pairs(1, 100000, cfg_id=5).to(DEV)
+    r = _subset_check(oracle, backend, b.src_des[0], b.tgt_des[0], rows=60)
+    assert int(r["n_mutual"].item()) == 100000
+    rm = backend.mutual_matching_device(b.src_des[0], b.tgt_des[0], b.src_xyz[0], b.tgt_xyz[0])
+    K = int(rm["n_mutual"].item())
+    off = torch.tensor([0, K], dtype=torch.int32, device=DEV); cnt = rm["n_mutual"]
+    H = 50000
+    whole = backend.ransac_batched(rm["corr"], off, cnt, H, 0.1, 0.8, seed=7)
+    parts = None
+    for rnk in range(4):
+        h0, h1 = rnk * H // 4, (rnk + 1) * H // 4
+        p = backend.ransac_batched(rm["corr"], off, cnt, H, 0.1, 0.8, seed=7, h_begin=h0, h_end=h1)
+        parts = p if parts is None else torch.maximum(parts, p)      # what all_reduce(MAX) does across ranks
+    assert torch.equal(parts, whole)
+    T, inl, bh = backend.ransac_finalize_batched(rm["corr"], off, cnt, whole, 0.1, 0.8, seed=7)
+    Tr, it, _ = backend.post_refinement_batched(T, rm["corr"], off, cnt, 0.1)
+    recall, rte, rre = S.registration_recall(Tr.cpu(), b.T_gt.cpu())
+    assert recall == 1.0 and int(inl) > 29000 and float(rte.max()) < 1e-3

@@ -33,6 +33,7 @@ SIGNATURES = {
     "bfr_get_matching_indices_workspace_bytes": (_sz, [_i]),
     "bfr_get_matching_indices": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_svd3_batched": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    "bfr_furthest_point_sample": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "bfr_fp32_probe": (_i, [_i, _i, _vp, _vp]),
     "bfr_debug_set_k1_events": (_i, [_vp, _vp]),
 }

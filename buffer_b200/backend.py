@@ -336,6 +336,21 @@ def svd(x):
     return u, s, v
 
 
+def furthest_point_sample(xyz, npoint):
+    """pointnet2_ops.furthest_point_sample drop-in (models/BUFFER.py:266-267): xyz [B,N,3] CUDA -> idx [B,npoint] int32"""
+    xyz = _f32c(xyz, "xyz")
+    B, N = xyz.shape[0], xyz.shape[1]
+    idx = torch.zeros(B, npoint, dtype=torch.int32, device=xyz.device)
+    temp = torch.empty(B, max(N, 1), dtype=torch.float32, device=xyz.device)
+    _lib.check(_lib.lib().bfr_furthest_point_sample(xyz.data_ptr(), B, N, int(npoint), idx.data_ptr(), temp.data_ptr(), _stream()), "bfr_furthest_point_sample")
+    return idx
+
+
+def gather_operation(features, idx):
+    """pointnet2_ops.gather_operation (models/BUFFER.py:268-271): features [B,C,N], idx [B,npoint] -> [B,C,npoint]; plain torch gather"""
+    return torch.gather(features, 2, idx.long()[:, None, :].expand(-1, features.shape[1], -1))
+
+
 def lrf_vote(ind, ss_R, tt_R, ss_kpts, tt_kpts, azi_n=20, inlier_th=1 / 3):
     """lines 294-311 of models/BUFFER.py in one call, everything stays on the device (no .cpu() at :311):
     -> R [A,3,3], t [A,3], inlier_num [A] int32, best_ind [1] int64, inlier_mask [A] bool"""

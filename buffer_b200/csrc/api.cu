@@ -242,6 +242,14 @@ int bfr_get_matching_indices(const float* source, int N, const float* target, in
     return cu(get_matching_indices_launch(source, N, target, M, relt_pose, search_voxel_size, match_inds, count, nn, dist, ws, st(stream)));
 }
 
+int bfr_furthest_point_sample(const float* xyz, int B, int N, int npoint, int32_t* idx, float* temp, void* stream)
+{
+    if (B == 0 || npoint == 0) return BFR_OK;
+    if (!xyz || !idx || !temp) return BFR_E_NULL;
+    if (B < 0 || N <= 0 || npoint < 0) return BFR_E_SIZE;
+    return cu(fps_launch(xyz, B, N, npoint, idx, temp, st(stream)));
+}
+
 int bfr_svd3_batched(const float* x, int B, float* u, float* s, float* v, void* stream)
 {
     if (B == 0) return BFR_OK;

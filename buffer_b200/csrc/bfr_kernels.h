@@ -44,6 +44,7 @@ cudaError_t post_refinement_launch(const float* T0, const float* corr, const int
 size_t knn3_workspace_bytes(int N);
 cudaError_t get_matching_indices_launch(const float* source, int N, const float* target, int M, const float* T, float voxel,
                                         int64_t* pairs, int32_t* count, int64_t* nn_out, float* dist_out, void* ws, cudaStream_t stream);
+cudaError_t fps_launch(const float* xyz, int B, int N, int npoint, int32_t* idx, float* temp, cudaStream_t stream);
 cudaError_t svd3_launch(const float* x, int B, float* u, float* s, float* v, cudaStream_t stream);
 
 }  // namespace bfr

@@ -153,6 +153,56 @@ __global__ void svd3_kernel(const float* __restrict__ x, int B, float* __restric
     for (int k = 0; k < 3; ++k) s[3 * (size_t)b + k] = si[k];
 }
 
+// ---- f4: farthest point sampling (pointnet2_ops.furthest_point_sample, reference models/BUFFER.py:266-267) ---------------
+// One CTA per cloud; the running min-distance array lives in the caller's workspace; each round every thread updates its
+// strided points and the CTA reduces (value, ~index) with a packed 64-bit max (ties -> lowest index).
+constexpr int FPS_THREADS = 1024;
+__global__ void __launch_bounds__(FPS_THREADS) fps_kernel(const float* __restrict__ xyz, int N, int npoint, int32_t* __restrict__ idx, float* __restrict__ temp)
+{
+    __shared__ unsigned long long red[FPS_THREADS / 32];
+    __shared__ int s_old;
+    const int b = blockIdx.x;
+    const float* p = xyz + (size_t)b * N * 3;
+    float* tmp = temp + (size_t)b * N;
+    int32_t* out = idx + (size_t)b * npoint;
+    for (int k = threadIdx.x; k < N; k += FPS_THREADS) tmp[k] = 1e10f;
+    if (threadIdx.x == 0) { out[0] = 0; s_old = 0; }
+    __syncthreads();
+    for (int j = 1; j < npoint; ++j) {
+        const int old = s_old;
+        const float x1 = p[3 * (size_t)old], y1 = p[3 * (size_t)old + 1], z1 = p[3 * (size_t)old + 2];
+        unsigned long long best = 0ull;                                  // (key(-1) would be smaller than any d2 >= 0 key; 0 = "none")
+        for (int k = threadIdx.x; k < N; k += FPS_THREADS) {
+            const float x2 = p[3 * (size_t)k], y2 = p[3 * (size_t)k + 1], z2 = p[3 * (size_t)k + 2];
+            const float mag = __fmaf_rn(z2, z2, __fmaf_rn(y2, y2, __fmul_rn(x2, x2)));
+            if (mag <= 1e-3f) continue;
+            const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1), dz = __fsub_rn(z2, z1);
+            const float d = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            const float d2 = d < tmp[k] ? d : tmp[k];
+            tmp[k] = d2;
+            const unsigned long long cand = pack_best(float_key(d2), (uint32_t)k);
+            best = cand > best ? cand : best;
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other > best ? other : best; }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned long long v = threadIdx.x < FPS_THREADS / 32 ? red[threadIdx.x] : 0ull;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o); v = other > v ? other : v; }
+            if (threadIdx.x == 0) { const int nxt = v ? (int)packed_index(v) : 0; s_old = nxt; out[j] = nxt; }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t fps_launch(const float* xyz, int B, int N, int npoint, int32_t* idx, float* temp, cudaStream_t stream)
+{
+    if (B > 0 && N > 0 && npoint > 0) fps_kernel<<<B, FPS_THREADS, 0, stream>>>(xyz, N, npoint, idx, temp);
+    return cudaGetLastError();
+}
+
 size_t knn3_workspace_bytes(int N) { return (size_t)(N > 0 ? N : 1) * 8 + 64; }
 
 cudaError_t get_matching_indices_launch(const float* source, int N, const float* target, int M, const float* T, float voxel,

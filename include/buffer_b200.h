@@ -133,6 +133,9 @@ size_t bfr_get_matching_indices_workspace_bytes(int N);
 int bfr_get_matching_indices(const float* source, int N, const float* target, int M, const float* relt_pose, float search_voxel_size,
                              int64_t* match_inds, int32_t* count, int64_t* nn, float* dist, void* ws, size_t ws_bytes, void* stream);
 int bfr_svd3_batched(const float* x, int B, float* u, float* s, float* v, void* stream);
+/* bfr_furthest_point_sample: pointnet2_ops.furthest_point_sample as called at models/BUFFER.py:266-267 (xyz [B][N][3] ->
+ * idx [B][npoint] int32, first index 0, points with |p|^2 <= 1e-3 skipped, ties -> lowest index); temp = [B][N] float scratch. */
+int bfr_furthest_point_sample(const float* xyz, int B, int N, int npoint, int32_t* idx, float* temp, void* stream);
 
 /* ---- measurement aids (used by bench.py only) ---------------------------------------------------------------------
  * bfr_fp32_probe: a pure FFMA2 stream on `grid` CTAs of 256 threads, executing grid*256*iters*256 FMAs (2 flop each);

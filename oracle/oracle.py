@@ -184,6 +184,15 @@ def get_matching_indices(source, target, relt_pose, search_voxel_size, want_nn=F
     return (pairs[:c].copy(), nn, dist) if want_nn else pairs[:c].copy()
 
 
+def furthest_point_sample(xyz, npoint):
+    """pointnet2_ops.furthest_point_sample restated (models/BUFFER.py:266-267): xyz [B,N,3] -> idx [B,npoint] int32"""
+    xyz = _f32(xyz); B, N, _ = xyz.shape
+    idx = np.zeros((B, npoint), np.int32)
+    for b in range(B):
+        lib().orc_furthest_point_sample(_p(xyz[b]), C.c_int(N), C.c_int(npoint), _p(idx[b]))
+    return idx
+
+
 def svd3(x):
     """batched 3x3 SVD (torch_batch_svd contract, utils/common.py:715): x [B,3,3] -> u [B,3,3], s [B,3] descending, v [B,3,3]"""
     x = _f32(x).reshape(-1, 9); B = x.shape[0]

@@ -256,6 +256,23 @@ def test_batched_svd3_bit_exact(oracle, backend):
     assert float((s.cpu().double() - ref).abs().max()) < 1e-5 * float(ref.max())
 
 
+def test_furthest_point_sample_bit_exact(oracle, backend):
+    g = torch.Generator().manual_seed(12)
+    xyz = torch.rand(3, 4000, 3, generator=g) * 3 - 1.5
+    xyz[1, :50] = 0.0                                               # |p|^2 <= 1e-3: skipped by pointnet2's kernel
+    xyz[2, 100] = xyz[2, 7]                                         # duplicate point
+    idx_o = oracle.furthest_point_sample(xyz.numpy(), 300)
+    idx = backend.furthest_point_sample(xyz.to(DEV), 300)
+    assert idx.dtype == torch.int32 and np.array_equal(idx.cpu().numpy(), idx_o)
+    assert len(set(idx_o[0].tolist())) == 300 and idx_o[0, 0] == 0
+    feats = xyz.transpose(1, 2).contiguous().to(DEV)
+    k = backend.gather_operation(feats, idx)
+    assert torch.equal(k[0, :, 5], xyz[0, idx_o[0, 5]].to(DEV))
+    # spread: sampled points cover the cloud far better than the first 300 points do
+    d = torch.cdist(xyz[0], xyz[0][idx_o[0].astype(np.int64)]).min(dim=1)[0].max()
+    assert float(d) < 0.45
+
+
 def test_lrf_vote_matches_separate_calls(backend):
     A = 300
     g = torch.Generator().manual_seed(4)

@@ -252,6 +252,20 @@ def main():
         r_tc = B.mutual_matching_batched(src_des, tgt_des, off, off, N, N, want_nn=True, want_mids=False)
         k1_paths_identical = bool(torch.equal(r_fp["nn_s"], r_tc["nn_s"]) and torch.equal(r_fp["nn_t"], r_tc["nn_t"]))
         del r_fp, r_tc
+        # ---- extra leg: K2+K3 alone on the same data (events on the launching stream), H_valid for the 28*H_valid*C work model --------
+        rm = B.mutual_matching_batched(src_des, tgt_des, off, off, N, N, src_xyz, tgt_xyz, want_nn=False, want_mids=False)
+        nvalid = torch.zeros(P, dtype=torch.int32, device=dev)
+        ransac_ms = []
+        for i in range(3):
+            nvalid.zero_()
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], seed=0, pair_id_base=rank * P, valid_count=nvalid)
+            eb.record(); eb.synchronize()
+            ransac_ms.append(ea.elapsed_time(eb))
+        ransac_ms = min(ransac_ms)
+        hv_total = float(nvalid.sum().item()); c_mean = float(rm["n_mutual"].float().mean().item())
+        del rm
 
     # ---- e2e: host (pinned) buffers -> poses on the host, copies inside the timed region ---------------------------
     e2e = None
@@ -311,6 +325,14 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, c, P), "clocks": clocks, "gpu_launches": (8 if args.k1_algo == 1 else 7) * args.steps,
                 "roofline": roof, "roofline_fp32_path": fp32_roof,
+                "roofline_ransac": {"kernel": "ransac_kernel (Philox + Kabsch + checkers + inlier scoring)", "bound": "fp32", "ms_per_launch": ransac_ms,
+                                    "valid_hypotheses_per_pair": hv_total / P, "hypotheses_per_pair": c["hypotheses"], "correspondences_per_pair": c_mean,
+                                    "algorithmic_flops_per_launch": 28.0 * hv_total * c_mean, "achieved": 28.0 * hv_total * c_mean / (ransac_ms * 1e-3) * 1e-12,
+                                    "peak": peak_tf, "unit": "TFLOP/s", "frac": 28.0 * hv_total * c_mean / (ransac_ms * 1e-3) * 1e-12 / peak_tf,
+                                    "hypotheses_per_s": P * c["hypotheses"] / (ransac_ms * 1e-3),
+                                    "streaming_model_gbs": 24.0 * c_mean * hv_total / 256.0 / (ransac_ms * 1e-3) * 1e-9,
+                                    "streaming_model_note": "bytes = 24*C*H_valid/T_h with T_h = 256 hypotheses per CTA pass; the correspondences stream from L2/shared memory, "
+                                                            "not HBM (compulsory HBM traffic is 32*C bytes per pair), so the kernel is FP32-issue-bound, not HBM-bound"},
                 "quality": {"registration_recall": recall, "rte_max_m": float(rte.max()), "rre_max_deg": float(rre.max()),
                             "mutual_matches_mean": float(nm.float().mean()), "ransac_inliers_mean": float(ni.float().mean())}}
         if e2e is not None:

@@ -154,7 +154,7 @@ def gather_corr(src_xyz, tgt_xyz, s_ids, t_ids):
 
 
 def ransac_batched(corr, corr_off, corr_cnt, hypotheses, dist_th, similar_th, seed=0, pair_id_base=0, h_begin=0, h_end=None,
-                   splits=None, best_packed=None):
+                   splits=None, best_packed=None, valid_count=None):
     """Evaluate hypotheses [h_begin, h_end) of every pair; max-accumulate into best_packed [P] (int64 view of the
     packed uint64 (count << 32) | (0xFFFFFFFF - h)).  Device only, no sync."""
     corr = _f32c(corr, "corr")
@@ -166,7 +166,7 @@ def ransac_batched(corr, corr_off, corr_cnt, hypotheses, dist_th, similar_th, se
         splits = max(1, min(64, (296 + P - 1) // max(P, 1)))
     _lib.check(_lib.lib().bfr_ransac_batched(corr.data_ptr(), corr_off.data_ptr(), corr_cnt.data_ptr(), P, int(seed), int(pair_id_base),
                                              int(h_begin), int(h_end), float(dist_th), float(similar_th), int(splits),
-                                             best_packed.data_ptr(), _stream()), "bfr_ransac_batched")
+                                             best_packed.data_ptr(), _ptr(valid_count), _stream()), "bfr_ransac_batched")
     return best_packed
 
 

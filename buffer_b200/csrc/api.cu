@@ -86,14 +86,14 @@ int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s
 
 int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
                        uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
-                       float dist_th, float similar_th, int splits, uint64_t* best_packed, void* stream)
+                       float dist_th, float similar_th, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream)
 {
     if (P == 0) return BFR_OK;
     if (!corr_xyz || !corr_off || !corr_cnt || !best_packed) return BFR_E_NULL;
     if (P < 0 || h_end < h_begin) return BFR_E_SIZE;
     if (!aligned16(corr_xyz)) return BFR_E_ALIGN;
     return cu(ransac_launch(corr_xyz, corr_off, corr_cnt, P, seed, pair_id_base, h_begin, h_end, dist_th, similar_th, splits,
-                            reinterpret_cast<unsigned long long*>(best_packed), st(stream)));
+                            reinterpret_cast<unsigned long long*>(best_packed), valid_count, st(stream)));
 }
 
 int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
@@ -174,7 +174,7 @@ int bfr_register_batched(const float* src_des, const float* src_xyz, const int32
     e = k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, total_M, total_N, D, 1, w.k1, nullptr, nullptr, nullptr, nullptr,
                   src_xyz, tgt_xyz, nullptr, nullptr, n_mutual, w.corr, s);
     if (e != cudaSuccess) return (int)e;
-    e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, ransac_splits, w.best, s);
+    e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, ransac_splits, w.best, nullptr, s);
     if (e != cudaSuccess) return (int)e;
     float* T_ransac = refine_iters > 0 ? w.T0 : T_out;
     e = ransac_finalize_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, dist_th, similar_th, w.best, T_ransac, n_inliers, nullptr, s);

@@ -26,7 +26,8 @@ void k1_set_events(cudaEvent_t e0, cudaEvent_t e1);
 
 // K2 + K3 (ransac.cu)
 cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
-                          uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, int splits, unsigned long long* best_packed, cudaStream_t stream);
+                          uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, int splits, unsigned long long* best_packed, int32_t* valid_count,
+                          cudaStream_t stream);
 cudaError_t ransac_finalize_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
                                    float dist_th, float similar_th, const unsigned long long* best_packed, float* T, int32_t* inliers, int64_t* best_h, cudaStream_t stream);
 cudaError_t lrf_hypotheses_launch(const float* cs, const float* ss_R, const float* tt_R, const float* ss_kpts, const float* tt_kpts, int A,

@@ -111,7 +111,7 @@ BFR_DEVINL void score_queue(RsSmem& sm, const float4* __restrict__ corr, int K, 
 __global__ void __launch_bounds__(RS_THREADS, 2)
 ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_off, const int32_t* __restrict__ corr_cnt,
               uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th,
-              unsigned long long* __restrict__ best_packed)
+              unsigned long long* __restrict__ best_packed, int32_t* __restrict__ valid_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RsSmem& sm = *reinterpret_cast<RsSmem*>(smem_raw);
@@ -129,6 +129,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
     if (threadIdx.x == 0) { sm.qcount = 0; sm.q1count = 0; }
     __syncthreads();
     unsigned long long best = 0ull;
+    int n_scored = 0;                                                 // hypotheses that passed every check (thread 0's tally)
 
     // stage 2 on n queue-1 entries (thread i takes entry i): Kabsch + distance check on dense warps, survivors -> queue 2;
     // scores a full block of queue 2 whenever one is available
@@ -161,6 +162,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         __syncthreads();
         if (qn >= RS_THREADS) {
             score_queue(sm, corr_p, K, RS_THREADS, d2max, best);
+            n_scored += RS_THREADS;
             const int rem = qn - RS_THREADS;                           // move the overflow [RS_THREADS, qn) down to the front
             float mv[12]; uint32_t mh = 0;
             if ((int)threadIdx.x < rem) {
@@ -212,7 +214,8 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         if (n1 > 0) fit_queue1(n1);
     }
     const int qn = sm.qcount;
-    if (qn > 0) score_queue(sm, corr_p, K, qn, d2max, best);
+    if (qn > 0) { score_queue(sm, corr_p, K, qn, d2max, best); n_scored += qn; }
+    if (valid_count && threadIdx.x == 0 && n_scored) atomicAdd(valid_count + p, n_scored);
 
     // block max -> one atomic
 #pragma unroll
@@ -364,7 +367,8 @@ static cudaError_t ensure_smem(const void* fn)
 }
 
 cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
-                          uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, int splits, unsigned long long* best_packed, cudaStream_t stream)
+                          uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, int splits, unsigned long long* best_packed, int32_t* valid_count,
+                          cudaStream_t stream)
 {
     static bool once = false;
     if (!once) { cudaError_t e = ensure_smem((const void*)ransac_kernel); if (e != cudaSuccess) return e; once = true; }
@@ -372,7 +376,7 @@ cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int3
     if (splits < 1) splits = 1;
     dim3 grid((unsigned)splits, (unsigned)P);
     ransac_kernel<<<grid, RS_THREADS, sizeof(RsSmem), stream>>>(reinterpret_cast<const float4*>(corr), corr_off, corr_cnt, seed, pair_id_base,
-                                                                h_begin, h_end, dist_th, similar_th, best_packed);
+                                                                h_begin, h_end, dist_th, similar_th, best_packed, valid_count);
     return cudaGetLastError();
 }
 

@@ -70,10 +70,12 @@ int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s
  * max_correspondence_distance = dist_th).  Evaluates hypotheses [h_begin, h_end) of every pair — hypothesis h of pair p
  * draws Philox4x32-10(key = seed, counter = (h, pair_id_base + p, 0, 0)) — and max-accumulates into best_packed[p] =
  * (inlier count << 32) | (0xFFFFFFFF - h): the caller zeroes best_packed before the first call and may split the
- * hypothesis range over several calls, streams or GPUs (all-reduce MAX) before finalising.  corr_cnt[p] < 3 leaves 0. */
+ * hypothesis range over several calls, streams or GPUs (all-reduce MAX) before finalising.  corr_cnt[p] < 3 leaves 0.
+ * valid_count (optional, [P] int32, zeroed by the caller) accumulates how many hypotheses passed every checker and were
+ * scored — the H_valid of the 28*H_valid*C scoring-work model. */
 int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
                        uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
-                       float dist_th, float similar_th, int splits, uint64_t* best_packed, void* stream);
+                       float dist_th, float similar_th, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream);
 /* Decode best_packed and regenerate the winning minimal-sample fit: T [P][16] row-major 4x4 (result.transformation,
  * models/BUFFER.py:326), inlier count and hypothesis index (-1 if none; T = identity). */
 int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,

@@ -117,9 +117,12 @@ def test_ransac_counts_and_fit_bit_exact(oracle, backend, N, H, rho):
         T_o, cnt_o, bh_o = oracle.ransac_finalize(corr, seed, 40 + p, best, 0.1, 0.8)
         cd = torch.from_numpy(corr).to(DEV)
         off = torch.tensor([0, len(s)], dtype=torch.int32, device=DEV); cnt = torch.tensor([len(s)], dtype=torch.int32, device=DEV)
+        _, counts_o = oracle.ransac(corr, seed, 40 + p, H, 0.1, 0.8, want_counts=True)
         for splits in (1, 7):
-            bp = backend.ransac_batched(cd, off, cnt, H, 0.1, 0.8, seed=seed, pair_id_base=40 + p, splits=splits)
+            nv = torch.zeros(1, dtype=torch.int32, device=DEV)
+            bp = backend.ransac_batched(cd, off, cnt, H, 0.1, 0.8, seed=seed, pair_id_base=40 + p, splits=splits, valid_count=nv)
             assert int(bp.item()) == best, (p, splits)
+            assert int(nv.item()) == int((counts_o >= 0).sum())      # same set of hypotheses passes the checkers
         T, inl, bh = backend.ransac_finalize_batched(cd, off, cnt, bp, 0.1, 0.8, seed=seed, pair_id_base=40 + p)
         assert int(inl.item()) == cnt_o and int(bh.item()) == bh_o
         assert np.array_equal(T[0].cpu().numpy(), T_o)            # same closed-form fit, bit for bit

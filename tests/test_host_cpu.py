@@ -68,7 +68,7 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.bfr_mutual_nn_workspace_bytes(2, 5000, 5000) >= 2 * 2 * 5120 * 12
     assert L.bfr_register_workspace_bytes(2, 100, 100, 200, 200) > 0 and L.bfr_score_workspace_bytes(10) >= 320
     assert L.bfr_mutual_matching_batched(None, None, None, None, 1, 1, 1, 1, 1, 32, 1, None, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
-    assert L.bfr_ransac_batched(None, None, None, 0, 0, 0, 0, 0, 0.1, 0.8, 1, None, None) == 0     # P == 0 is a no-op
+    assert L.bfr_ransac_batched(None, None, None, 0, 0, 0, 0, 0, 0.1, 0.8, 1, None, None, None) == 0     # P == 0 is a no-op
     assert L.bfr_rigid_transform_3d(None, None, None, 3, 3, 0.0, None, None) == -1
 
 

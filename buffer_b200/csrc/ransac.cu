@@ -48,6 +48,12 @@ BFR_DEVINL void load_chunk(RsSmem& sm, const float4* __restrict__ corr, int K, i
     }
 }
 
+// ++count iff d < thr, as one FSETP + one predicated IADD (the compiler's select form costs an extra add per test)
+BFR_DEVINL void count_if_lt(int& count, float d, float thr)
+{
+    asm("{\n\t.reg .pred q;\n\tsetp.lt.f32 q, %1, %2;\n\t@q add.s32 %0, %0, 1;\n\t}" : "+r"(count) : "f"(d), "f"(thr));
+}
+
 // inlier count of one hypothesis over the chunk currently in shared memory (npairs pairs of correspondences)
 template <bool PER_CORR_THR>
 BFR_DEVINL int score_chunk(const RsSmem& sm, int npairs, const float R[9], const float t[3], float d2max)
@@ -71,11 +77,11 @@ BFR_DEVINL int score_chunk(const RsSmem& sm, int npairs, const float R[9], const
         unpack2(d2, da, db);
         if (PER_CORR_THR) {
             const float2 w = *reinterpret_cast<const float2*>(&sm.chunk[g][3]);
-            count += (da < w.x) ? 1 : 0;
-            count += (db < w.y) ? 1 : 0;
+            count_if_lt(count, da, w.x);
+            count_if_lt(count, db, w.y);
         } else {
-            count += (da < d2max) ? 1 : 0;
-            count += (db < d2max) ? 1 : 0;
+            count_if_lt(count, da, d2max);
+            count_if_lt(count, db, d2max);
         }
     }
     return count;

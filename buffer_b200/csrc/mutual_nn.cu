@@ -38,9 +38,10 @@ struct __align__(128) K1Smem {
     int done[K1_STAGES];                      // warps that have finished reading the stage; the last one refills it
 };
 
-// ---- prep: half squared norms into the padded workspace (-inf in the padding) and zeroed packed bests ------------
+// ---- prep: half squared norms into the padded workspace (-inf in the padding), zeroed packed bests and -- for the tensor-core
+// path -- a bf16 (round-to-nearest-even) copy of the descriptors, row o + i of the concatenated array -> row o + i of xb ----------
 __global__ void __launch_bounds__(256) k1_prep_kernel(const float* __restrict__ x, const int32_t* __restrict__ off, int P, int D, int pad,
-                                                      float* __restrict__ hn, unsigned long long* __restrict__ packed)
+                                                      float* __restrict__ hn, unsigned long long* __restrict__ packed, uint4* __restrict__ xb)
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)P * pad) return;
@@ -50,7 +51,27 @@ __global__ void __launch_bounds__(256) k1_prep_kernel(const float* __restrict__ 
     if (i < n) {
         const float* row = x + (size_t)(o + i) * D;
         float s = 0.0f;
-        if ((D & 3) == 0) {
+        if (D == K1_D) {
+            float4 v[K1_D / 4];
+#pragma unroll
+            for (int k = 0; k < K1_D / 4; ++k) v[k] = __ldg(reinterpret_cast<const float4*>(row) + k);
+#pragma unroll
+            for (int k = 0; k < K1_D / 4; ++k) {
+                s = __fmaf_rn(v[k].x, v[k].x, s); s = __fmaf_rn(v[k].y, v[k].y, s); s = __fmaf_rn(v[k].z, v[k].z, s); s = __fmaf_rn(v[k].w, v[k].w, s);
+            }
+            if (xb) {
+                uint4* dst = xb + (size_t)(o + i) * (K1_D / 8);
+#pragma unroll
+                for (int k = 0; k < K1_D / 8; ++k) {
+                    uint4 w;
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v[2 * k].y), "f"(v[2 * k].x));       // low half = first element
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v[2 * k].w), "f"(v[2 * k].z));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.z) : "f"(v[2 * k + 1].y), "f"(v[2 * k + 1].x));
+                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.w) : "f"(v[2 * k + 1].w), "f"(v[2 * k + 1].z));
+                    dst[k] = w;
+                }
+            }
+        } else if ((D & 3) == 0) {
             for (int k = 0; k < D; k += 4) {
                 const float4 v = __ldg(reinterpret_cast<const float4*>(row + k));
                 s = __fmaf_rn(v.x, v.x, s); s = __fmaf_rn(v.y, v.y, s); s = __fmaf_rn(v.z, v.z, s); s = __fmaf_rn(v.w, v.w, s);
@@ -339,7 +360,8 @@ int k1_pad_rows(int max_rows) { return round_up(max_rows > 0 ? max_rows : 1, K1_
 size_t k1_workspace_bytes(int P, int max_M, int max_N)
 {
     const size_t padM = (size_t)k1_pad_rows(max_M), padN = (size_t)k1_pad_rows(max_N);
-    return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long)) + 256;
+    // packed bests + half norms + (tensor-core path) bf16 copies of both descriptor sets (<= P * pad rows of 64 bytes each)
+    return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long) + (size_t)K1_D * 2) + 512;
 }
 
 static int g_k1_algo = 1;                       // 0 = FP32 FFMA2 kernel, 1 = tensor-core filter + exact re-check (mutual_nn_tc.cu)
@@ -359,12 +381,16 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     unsigned long long* row_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * padM * 8;
     unsigned long long* col_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * padN * 8;
     float* hna = reinterpret_cast<float*>(w); w += (size_t)P * padM * 4;
-    float* hnb = reinterpret_cast<float*>(w);
+    float* hnb = reinterpret_cast<float*>(w); w += (size_t)P * padN * 4;
+    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    uint4* src_bf = reinterpret_cast<uint4*>(w); w += (size_t)P * padM * K1_D * 2;          // total_M <= P * padM rows
+    uint4* tgt_bf = reinterpret_cast<uint4*>(w);
+    const bool tc = g_k1_algo == 1 && max_M > 0 && max_N > 0 && k1_tc_supported(D, total_M, total_N);
 
     {
         const long long na = (long long)P * padM, nb = (long long)P * padN;
-        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed);
-        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed);
+        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed, tc ? src_bf : nullptr);
+        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed, tc ? tgt_bf : nullptr);
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -376,8 +402,8 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     dim3 grid((unsigned)((max_M + K1_ROWS - 1) / K1_ROWS), (unsigned)col_splits, (unsigned)P);
     if (g_k1_ev0) cudaEventRecord(g_k1_ev0, stream);
     if (max_M > 0 && max_N > 0) {
-        if (g_k1_algo == 1 && k1_tc_supported(D, total_M, total_N)) {
-            cudaError_t e = k1_tc_launch(src, tgt, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
+        if (tc) {
+            cudaError_t e = k1_tc_launch(src, tgt, src_bf, tgt_bf, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
             if (e != cudaSuccess) return e;
         } else {
             k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);

@@ -30,35 +30,88 @@ namespace bfr {
 constexpr int TC_BM = 256;                      // own rows per CTA = two M=128 accumulator halves sharing every streamed tile
 constexpr int TC_BN = 128;                      // streamed rows per tile (MMA N)
 constexpr int TC_D = 32;
-constexpr int TC_STAGES = 4;
+#ifndef TC_MMAK
+#define TC_MMAK (TC_D / 16)
+#endif
+#ifndef TC_STAGES_N
+#define TC_STAGES_N 4
+#endif
+#ifndef TC_CAP_N
+#define TC_CAP_N 14
+#endif
+constexpr int TC_STAGES = TC_STAGES_N;
 constexpr int TC_EPI_WARPS = 8;                 // one epilogue thread per own row
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+#ifndef TC_EXP
+#define TC_EXP 0
+#endif
 constexpr int TC_SUB = 4;                       // candidate granularity: 4-column groups
-constexpr int TC_CAP = 24;                      // candidate groups kept per row
-constexpr int TC_MAX_TILES = 64;                // streamed tiles per CTA (hn cache = 8192 floats)
+constexpr int TC_CAP = TC_CAP_N;                      // band events (32-column chunks with their 8 group maxima) kept per row
+constexpr int TC_GCAP = 32;                     // surviving 4-column groups per row handed to the exact re-check
+constexpr int TC_MAX_TILES = 48;                // streamed tiles per CTA (hn cache = 6144 floats)
+
+#ifdef TC_TIMING
+__device__ unsigned long long g_dbg[8];
+#endif
 
 struct TcSmem {
-    float a[TC_BM * TC_D];                      // 32 KB, SWIZZLE_128B K-major (one 128-byte atom per row); rows 128.. = second half
-    float b[TC_STAGES][TC_BN * TC_D];           // 4 x 16 KB
+    uint16_t a[TC_BM * TC_D];                   // 16 KB bf16, SWIZZLE_64B K-major (one 64-byte row per descriptor); rows 128.. = second half
+    uint16_t b[TC_STAGES][TC_BN * TC_D];        // 4 x 8 KB (after the last MMA: uint32_t glist[TC_GCAP][TC_BM], the groups to re-check)
     float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
-    uint2 cand[TC_CAP][TC_BM];                  // candidate groups [slot][row]: {approximate group maximum (float bits), first streamed column}
+    float4 cmg[TC_EPI_WARPS][TC_CAP][2][32];    // band events [warp][slot][half][lane]: the eight 4-column group maxima of the chunk
+                                                // (once a warp has consumed its events: that warp's 8 KB staging area of the re-check)
+    uint2 cid[TC_EPI_WARPS][TC_CAP][32];        //   ... {chunk maximum (float bits), CTA-local first streamed column of the chunk}
     float red[TC_THREADS / 32], red2[TC_THREADS / 32];
     uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
 };
+static_assert(sizeof(uint16_t) * TC_STAGES * TC_BN * TC_D >= sizeof(uint32_t) * TC_GCAP * TC_BM, "group list must fit in the TMA ring");
+static_assert(TC_CAP * 2 * 32 * sizeof(float4) >= 2 * 256 * sizeof(float4), "a warp's event slice doubles as its 8 KB staging area");
+constexpr uint32_t TC_CMG_HALF = sizeof(float4) * 32;           // 512: second half of an event's group maxima
+constexpr uint32_t TC_CMG_SLOT = 2 * TC_CMG_HALF;               // 1024
+constexpr uint32_t TC_CID_SLOT = sizeof(uint2) * 32;            // 256
+
+// Hot-loop append, fully predicated (no branch): if (c >= thr) { event slot <- (mg[0..7], c, id); advance both slot pointers }.
+// p16 / p8 are the shared-memory addresses of this row's next free slot in cmg / cid.
+BFR_DEVINL void append_if_in_band(float c, float thr, uint32_t& p16, uint32_t& p8, const float (&mg)[8], uint32_t id)
+{
+#ifdef TC_BRANCH_APPEND
+    if (c >= thr) {
+        asm volatile("st.shared.v4.f32 [%0], {%2, %3, %4, %5};\n\t"
+                     "st.shared.v4.f32 [%0+512], {%6, %7, %8, %9};\n\t"
+                     "st.shared.v2.b32 [%1], {%10, %11};"
+                     :: "r"(p16), "r"(p8), "f"(mg[0]), "f"(mg[1]), "f"(mg[2]), "f"(mg[3]), "f"(mg[4]), "f"(mg[5]), "f"(mg[6]), "f"(mg[7]),
+                        "r"(__float_as_uint(c)), "r"(id) : "memory");
+        p16 += 1024; p8 += 256;
+    }
+    return;
+#endif
+    asm volatile("{\n\t.reg .pred q;\n\t"
+                 "setp.ge.f32 q, %2, %3;\n\t"
+                 "@q st.shared.v4.f32 [%0], {%4, %5, %6, %7};\n\t"
+                 "@q st.shared.v4.f32 [%0+512], {%8, %9, %10, %11};\n\t"
+                 "@q st.shared.v2.b32 [%1], {%12, %13};\n\t"
+                 "@q add.u32 %0, %0, 1024;\n\t"
+                 "@q add.u32 %1, %1, 256;\n\t}"
+                 : "+r"(p16), "+r"(p8)
+                 : "f"(c), "f"(thr), "f"(mg[0]), "f"(mg[1]), "f"(mg[2]), "f"(mg[3]), "f"(mg[4]), "f"(mg[5]), "f"(mg[6]), "f"(mg[7]),
+                   "r"(__float_as_uint(c)), "r"(id)
+                 : "memory");
+}
+static_assert(TC_CMG_HALF == 512 && TC_CMG_SLOT == 1024 && TC_CID_SLOT == 256, "append_if_in_band hard-codes these strides");
 
 BFR_DEVINL void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-BFR_DEVINL uint64_t umma_desc_sw128(const void* smem)
-{   // K-major, SWIZZLE_128B: 8-row groups 1024 B apart (SBO = 64 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell)
-    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+BFR_DEVINL uint64_t umma_desc_sw64(const void* smem)
+{   // K-major, SWIZZLE_64B: 8-row groups 512 B apart (SBO = 32 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell), layout 4 = SW64
+    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
-BFR_DEVINL void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+BFR_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 BFR_DEVINL void umma_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
@@ -82,6 +135,16 @@ BFR_DEVINL void tmem_ld32_issue(uint32_t taddr, float (&v)[32])
 BFR_DEVINL void tmem_ld_wait(float (&v)[32])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
+                   "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]),
+                   "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
+                 :: "memory");
+}
+
+// no instruction: orders the uses of a second in-flight buffer after the tcgen05.wait::ld issued just before (volatile asm keeps program order)
+BFR_DEVINL void tmem_ld_pin(float (&v)[32])
+{
+    asm volatile(""
                  : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
                    "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]),
                    "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
@@ -113,7 +176,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];      // no static shared memory in this kernel: base is 1024-aligned
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
-    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();                 // SWIZZLE_128B atoms need 1024-byte alignment
+    if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();                 // swizzle atoms need (at least) 512-byte alignment
 
     const int p = blockIdx.z;
     const int oo = off_own[p], M = off_own[p + 1] - oo;
@@ -130,7 +193,10 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* hn_str_p = hn_str + (size_t)p * pad_str;
 #ifdef TC_TIMING
-    long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0;
+    long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq_wait = 0, tq_ld = 0, tq_proc = 0, tq_cmp = 0;
+#define TCT(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
+#else
+#define TCT(acc, stmt) { stmt; }
 #endif
 
     // ---- setup: barriers, TMEM, streamed half-norms (+ their minimum = largest streamed norm) ----------------------
@@ -168,21 +234,21 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            mbar_expect_tx(&sm.a_full, TC_BM * TC_D * 4);
+            mbar_expect_tx(&sm.a_full, TC_BM * TC_D * 2);
             tma_load_2d(sm.a, &map_own, 0, oo + row0, &sm.a_full);
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(&sm.empty[s], ph ^ 1u);
-                mbar_expect_tx(&sm.full[s], TC_BN * TC_D * 4);
+                mbar_expect_tx(&sm.full[s], TC_BN * TC_D * 2);
                 tma_load_2d(sm.b[s], &map_str, 0, os + (t_begin + it) * TC_BN, &sm.full[s]);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint64_t adesc0 = umma_desc_sw128(sm.a), adesc1 = umma_desc_sw128(sm.a + 128 * TC_D);
+            // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint64_t adesc0 = umma_desc_sw64(sm.a), adesc1 = umma_desc_sw64(sm.a + 128 * TC_D);
             mbar_wait(&sm.a_full, 0);
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
@@ -190,13 +256,13 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                 mbar_wait(&sm.full[s], ph);
                 mbar_wait(&sm.acc_empty[a], aph ^ 1u);
                 tc_fence_after();
-                const uint64_t bdesc = umma_desc_sw128(sm.b[s]);
+                const uint64_t bdesc = umma_desc_sw64(sm.b[s]);
                 for (int h = 0; h < halves; ++h) {
                     const uint32_t d = tmem_base + (uint32_t)((a * 2 + h) * TC_BN);
                     const uint64_t ad = h ? adesc1 : adesc0;
 #pragma unroll
-                    for (int k = 0; k < TC_D / 8; ++k)               // +32 bytes (2 x 16 B) per K step inside the swizzle atom
-                        umma_tf32(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < TC_MMAK; ++k)              // K = 16 per instruction: +32 bytes (2 x 16 B) per step inside the 64-byte row
+                        umma_bf16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
                 }
                 umma_commit(&sm.empty[s]);
                 umma_commit(&sm.acc_full[a]);
@@ -210,14 +276,19 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         const int row = row0 + r;
         const bool valid = row < M;
         const float own_hn = valid ? hn_own[(size_t)p * pad_own + row] : 0.0f;
-        const float two_eps = 0.0078125f * sqrtf(fmaxf(-2.0f * own_hn, 0.0f) * fmaxf(str_max_sq, 0.0f)) + 1e-30f;   // 2 * 2^-8 |a| max|b|
+        const float two_eps = 0.016f * sqrtf(fmaxf(-2.0f * own_hn, 0.0f) * fmaxf(str_max_sq, 0.0f)) + 1e-30f;      // 2 eps, eps = 1.024 * 2^-7 |a| max|b|
         // Streamed norms (nearly) uniform -- L2-normalised descriptors, BUFFER's case: rank full tiles on the raw dot products
         // (no hn add) and widen the band by the spread of hn; scores of hn-adjusted (partial) tiles are shifted by -hmax to match.
         const bool uniform = hn_spread <= 0.0009765625f * str_max_sq;   // CTA-uniform (the branch below contains warp-collective TMEM loads)
-        const float band = uniform ? two_eps + hn_spread : two_eps;
-        float m_run = -INFINITY; int cnt = 0; bool overflow = false;
+        const float band = !valid ? -INFINITY : uniform ? two_eps + hn_spread : two_eps;     // rows beyond M never record an event
+        float m_run = -INFINITY, dropped_max = -INFINITY;
+        const int ew = warp - 2;                                      // epilogue warp index: owns sm.cmg[ew] / sm.cid[ew]
+        const uint32_t p16_base = smem_u32(&sm.cmg[ew][0][0][lane]), p8_base = smem_u32(&sm.cid[ew][0][lane]);
+        uint32_t p16 = p16_base, p8 = p8_base;                        // next free event slot of this row
+        const uint32_t p8_high = p8_base + (uint32_t)(TC_CAP - 4) * TC_CID_SLOT;   // a tile appends at most 4 events
 
-        // one 32-column chunk: (add hn(b_j),) 4-column group maxima, running maximum, predicated append of in-band groups
+        // one 32-column chunk: (add hn(b_j),) 4-column group maxima -> chunk maximum -> running maximum; if the chunk maximum is inside
+        // the band the eight group maxima are kept as one event (predicated stores, no branch)
         auto process = [&](float (&v)[32], int colbase, auto raw_tag) {
             constexpr bool RAW = decltype(raw_tag)::value;            // RAW: v stays the bare dot product, compared in "dot + hmax" units
             if (!RAW) {
@@ -228,56 +299,96 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                     unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
                 }
             }
+#if TC_EXP == 7
+            m_run = fmaxf(m_run, v[0] + v[31]); return;
+#endif
             float mg[8];                                              // maxima of the eight 4-column groups, in raw dot-product units
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 mg[k] = fmaxf(max3(v[4 * k], v[4 * k + 1], v[4 * k + 2]), v[4 * k + 3]);
                 if (!RAW) mg[k] -= hmax;                              // hn-adjusted tiles: shift so that both kinds of tile compare
             }
-            m_run = fmaxf(m_run, fmaxf(max3(max3(mg[0], mg[1], mg[2]), mg[3], mg[4]), max3(mg[5], mg[6], mg[7])));
-            const float thr = m_run - band;
-            if (cnt > TC_CAP - 8) {                                   // rare: compact the list against the current band
-                int n = 0;
-                for (int k = 0; k < cnt; ++k) {
-                    const uint2 e = sm.cand[k][r];
-                    if (__uint_as_float(e.x) >= thr) { sm.cand[n][r] = e; ++n; }
-                }
-                cnt = n;
-                if (cnt > TC_CAP - 8) { overflow = true; cnt = 0; }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {                             // predicated append of the groups inside the band (one 64-bit store each)
-                if (mg[k] >= thr) { sm.cand[cnt][r] = make_uint2(__float_as_uint(mg[k]), (uint32_t)(t_begin * TC_BN + colbase + 4 * k)); ++cnt; }
-            }
+            const float c = fmaxf(max3(max3(mg[0], mg[1], mg[2]), mg[3], mg[4]), max3(mg[5], mg[6], mg[7]));
+            m_run = fmaxf(m_run, c);
+#if TC_EXP == 8
+            return;
+#endif
+            append_if_in_band(c, m_run - band, p16, p8, mg, (uint32_t)colbase);
         };
+        // rare (per lane, once the slots run low): drop the events that fell out of the band.  If more than TC_CAP - 4 survive (the running
+        // maximum is still creeping up through typical chunk maxima) the lowest ones are dropped too and their maximum remembered: the row
+        // only needs the exact scan if that maximum is still inside the band at the very end.
+        auto compact = [&]() {
+            const float thr = m_run - band;
+            const int cnt = (int)((p8 - p8_base) / TC_CID_SLOT);
+            int n = 0;
+            for (int k = 0; k < cnt; ++k) {
+                const uint2 e = sm.cid[ew][k][lane];
+                if (__uint_as_float(e.x) >= thr) {
+                    if (n != k) { sm.cid[ew][n][lane] = e; sm.cmg[ew][n][0][lane] = sm.cmg[ew][k][0][lane]; sm.cmg[ew][n][1][lane] = sm.cmg[ew][k][1][lane]; }
+                    ++n;
+                }
+            }
+#ifdef TC_TIMING
+            atomicAdd(&g_dbg[0], 1ull); atomicAdd(&g_dbg[1], (unsigned long long)cnt); atomicAdd(&g_dbg[2], (unsigned long long)n);
+            if (n > TC_CAP - 4) atomicAdd(&g_dbg[valid ? 3 : 4], 1ull);
+#endif
+            while (n > TC_CAP - 4) {
+                int jmin = 0; float cmin = __uint_as_float(sm.cid[ew][0][lane].x);
+                for (int k = 1; k < n; ++k) { const float ck = __uint_as_float(sm.cid[ew][k][lane].x); if (ck < cmin) { cmin = ck; jmin = k; } }
+                dropped_max = fmaxf(dropped_max, cmin);
+                --n;
+                if (jmin != n) { sm.cid[ew][jmin][lane] = sm.cid[ew][n][lane]; sm.cmg[ew][jmin][0][lane] = sm.cmg[ew][n][0][lane]; sm.cmg[ew][jmin][1][lane] = sm.cmg[ew][n][1][lane]; }
+            }
+            p16 = p16_base + (uint32_t)n * TC_CMG_SLOT; p8 = p8_base + (uint32_t)n * TC_CID_SLOT;
+        };
+        // Software pipeline across tiles: while chunks (2,3) of tile `it` are reduced, chunks (0,1) of tile it+1 are already in flight, so the
+        // TMEM -> register latency never sits on the critical path of the two epilogue warps that share a scheduler.
         const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int it = 0; it < ntiles; ++it) {
-            const int a = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-            mbar_wait(&sm.acc_full[a], aph);
+        auto tile_addr = [&](int it) { return lane_base + (uint32_t)(((it & 1) * 2 + half) * TC_BN); };
+        auto acc_wait = [&](int it) {
+#ifdef TC_TIMING
+            const long long tw0 = clock64();
+#endif
+            mbar_wait(&sm.acc_full[it & 1], (uint32_t)(it >> 1) & 1u);
+#ifdef TC_TIMING
+            tq_wait += clock64() - tw0;
+#endif
             tc_fence_after();
             __syncwarp();
-            const uint32_t t0 = lane_base + (uint32_t)((a * 2 + half) * TC_BN);
+        };
+        float va[32], vb[32], vc[32], vd[32];
+        acc_wait(0);
+        tmem_ld32_issue(tile_addr(0), va); tmem_ld32_issue(tile_addr(0) + 32, vb);
+        for (int it = 0; it < ntiles; ++it) {
+            const uint32_t t0 = tile_addr(it);
             const int cb = it * TC_BN;                                // CTA-local streamed column of this tile
-            float va[32], vb[32];                                     // software pipeline: load chunk c+1 while chunk c is processed
             const bool raw = uniform && (t_begin + it + 1) * TC_BN <= N;   // full tile (no padding columns to mask) and uniform norms
-            tmem_ld32_issue(t0, va);      tmem_ld_wait(va);
-            if (raw) {
-                tmem_ld32_issue(t0 + 32, vb); process(va, cb, std::true_type{});      tmem_ld_wait(vb);
-                __syncwarp();
-                tmem_ld32_issue(t0 + 64, va); process(vb, cb + 32, std::true_type{}); tmem_ld_wait(va);
-                __syncwarp();
-                tmem_ld32_issue(t0 + 96, vb); process(va, cb + 64, std::true_type{}); tmem_ld_wait(vb);
-            } else {
-                tmem_ld32_issue(t0 + 32, vb); process(va, cb, std::false_type{});      tmem_ld_wait(vb);
-                __syncwarp();
-                tmem_ld32_issue(t0 + 64, va); process(vb, cb + 32, std::false_type{}); tmem_ld_wait(va);
-                __syncwarp();
-                tmem_ld32_issue(t0 + 96, vb); process(va, cb + 64, std::false_type{}); tmem_ld_wait(vb);
-            }
+            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb));
+            tmem_ld32_issue(t0 + 64, vc); tmem_ld32_issue(t0 + 96, vd);
+            TCT(tq_proc,
+            if (raw) { process(va, cb, std::true_type{}); process(vb, cb + 32, std::true_type{}); }
+            else { process(va, cb, std::false_type{}); process(vb, cb + 32, std::false_type{}); })
+            TCT(tq_ld, tmem_ld_wait(vc); tmem_ld_pin(vd));
             tc_fence_before();                                        // all TMEM reads of this accumulator are complete
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.acc_empty[a]);             // the MMA warp may overwrite it while the last chunk is processed
-            if (raw) process(vb, cb + 96, std::true_type{}); else process(vb, cb + 96, std::false_type{});
+            if (lane == 0) mbar_arrive(&sm.acc_empty[it & 1]);        // the MMA warp may overwrite it while the last chunks are reduced
+            if (it + 1 < ntiles) {
+                acc_wait(it + 1);
+                tmem_ld32_issue(tile_addr(it + 1), va); tmem_ld32_issue(tile_addr(it + 1) + 32, vb);
+            }
+            TCT(tq_proc,
+            if (raw) { process(vc, cb + 64, std::true_type{}); process(vd, cb + 96, std::true_type{}); }
+            else { process(vc, cb + 64, std::false_type{}); process(vd, cb + 96, std::false_type{}); })
+#if TC_EXP == 10
+            if (p8 > p8_high) { p16 = p16_base; p8 = p8_base; }
+#else
+#if TC_EXP == 12
+            if (p8 > p8_high) { if (ntiles > 100000) compact(); else { p16 = p16_base; p8 = p8_base; } }
+#else
+            TCT(tq_cmp, if (p8 > p8_high) compact());
+#endif
+#endif
         }
 
 #ifdef TC_TIMING
@@ -285,10 +396,33 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 #endif
         // ---- exact FP32 re-check of the surviving groups (or of the whole row after an overflow) ---------------------------
         // One lane = one row, but the candidate rows are fetched cooperatively: 8 lanes read the 8 float4 of one 128-byte row
-        // (coalesced, 4 rows per warp-wide load) and transpose through an XOR-swizzled per-warp staging area carved out of the
-        // now idle TMA ring, so that the L1 sees 4 wavefronts per load instruction instead of 32.
+        // (coalesced, 4 rows per warp-wide load) and transpose through an XOR-swizzled per-warp staging area (the warp's own event
+        // slice, dead once the group list is built), so that the L1 sees 4 wavefronts per load instruction instead of 32.
         {
-            float4* stage = reinterpret_cast<float4*>(&sm.b[0][0]) + (warp - 2) * 512;     // 2 buffers x (32 rows x 8 float4)
+            const float thr = m_run - band;
+            bool overflow = dropped_max >= thr;                       // a dropped event could still hold the maximum: exact scan of the row
+            const int j_end = min(N, t_end * TC_BN);
+            float best = -INFINITY; int best_j = 0x7fffffff;
+            // surviving events -> list of in-band 4-column groups (global streamed column of each), in the idle TMA ring
+            uint32_t (*glist)[TC_BM] = reinterpret_cast<uint32_t (*)[TC_BM]>(&sm.b[0][0]);
+            int n = 0;
+            if (valid && !overflow && TC_EXP != 10 && TC_EXP != 11 && TC_EXP != 12) {
+                const int cnt = (int)((p8 - p8_base) / TC_CID_SLOT);
+                for (int k = 0; k < cnt && !overflow; ++k) {
+                    const uint2 e = sm.cid[ew][k][lane];
+                    if (__uint_as_float(e.x) < thr) continue;
+                    const float4 g0 = sm.cmg[ew][k][0][lane], g1 = sm.cmg[ew][k][1][lane];
+                    const float mg[8] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w };
+#pragma unroll
+                    for (int g = 0; g < 8; ++g)
+                        if (mg[g] >= thr) {
+                            if (n < TC_GCAP) glist[n++][r] = (uint32_t)(t_begin * TC_BN) + e.y + 4u * (uint32_t)g; else overflow = true;
+                        }
+                }
+                if (overflow) n = 0;
+            }
+            __syncwarp();                                             // every lane is done with its events: the slice becomes the staging area
+            float4* stage = &sm.cmg[ew][0][0][0];                     // 2 buffers x (32 rows x 8 float4)
             const int sub = lane >> 3, chunk = lane & 7;
             // gather 32 rows (one per lane, row index `want`, -1 = none) of `base` into registers, 4 rows per instruction
             auto fetch = [&](const float* __restrict__ base, int want, float4 (&reg)[8]) {
@@ -308,26 +442,16 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                 for (int c = 0; c < 8; ++c) rowv[c] = stage[buf * 256 + lane * 8 + (c ^ (lane & 7))];
             };
             float4 own[8], reg[8];
-            __syncwarp();
             fetch(x_own + (size_t)oo * TC_D, valid ? row : -1, reg);
             put(0, reg);
             __syncwarp();
             get(0, own);
             __syncwarp();
-            const float thr = m_run - band;
-            const int j_end = min(N, t_end * TC_BN);
-            float best = -INFINITY; int best_j = 0x7fffffff;
-            int n = 0;                                                // compact the survivors so that the warp's lanes stay aligned
-            if (valid && !overflow)
-                for (int k = 0; k < cnt; ++k) {
-                    const uint2 e = sm.cand[k][r];
-                    if (__uint_as_float(e.x) >= thr) { sm.cand[n][r] = e; ++n; }
-                }
             const int nmax = __reduce_max_sync(0xffffffffu, n);
             const float* xs = x_str + (size_t)os * TC_D;
             auto column = [&](int k, int u) {                         // streamed column this lane evaluates in sub-round (k, u), or -1
                 if (k >= n) return -1;
-                const int j = (int)sm.cand[k][r].y + u;
+                const int j = (int)glist[k][r] + u;
                 return j < j_end ? j : -1;
             };
             const int rounds = nmax * TC_SUB;
@@ -370,11 +494,16 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     __syncthreads();
 #ifdef TC_TIMING
     tq4 = clock64();
-    if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && (warp == 2 || warp == 9)) printf("cta %d warp %d: setup %lld main %lld verify %lld tailwait %lld\n", blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq3 - tq2, tq4 - tq3);
+    if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && (warp == 2 || warp == 9)) printf("cta %d warp %d: setup %lld main %lld (acc wait %lld ldwait %lld proc %lld compact %lld) verify %lld tailwait %lld\n", blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq_wait, tq_ld, tq_proc, tq_cmp, tq3 - tq2, tq4 - tq3);
 #endif
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
 
+#ifdef TC_TIMING
+}
+extern "C" __attribute__((visibility("default"))) void bfr_dbg_counters(unsigned long long* out) { cudaMemcpyFromSymbol(out, bfr::g_dbg, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(bfr::g_dbg, z, 64); }
+namespace bfr {
+#endif
 // ---- host side ----------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -390,28 +519,28 @@ static EncodeTiledFn encode_fn()
     return fn;
 }
 
-static bool make_map(CUtensorMap* map, const float* base, long long rows, int box_rows)
+static bool make_map(CUtensorMap* map, const void* base, long long rows, int box_rows)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = { (cuuint64_t)TC_D, (cuuint64_t)rows };
-    cuuint64_t strides[1] = { (cuuint64_t)TC_D * 4 };
+    cuuint64_t strides[1] = { (cuuint64_t)TC_D * 2 };
     cuuint32_t box[2] = { (cuuint32_t)TC_D, (cuuint32_t)box_rows };
     cuuint32_t estr[2] = { 1, 1 };
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool k1_tc_supported(int D, long long total_M, long long total_N) { return D == TC_D && total_M > 0 && total_N > 0 && encode_fn() != nullptr; }
 
 // both directions; hna/hnb/row_packed/col_packed are the (prepared, zeroed) workspace arrays of k1_launch
-cudaError_t k1_tc_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_bf16, const void* tgt_bf16, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
                          long long total_M, long long total_N, const float* hna, const float* hnb, int padM, int padN,
                          unsigned long long* row_packed, unsigned long long* col_packed, cudaStream_t stream)
 {
     CUtensorMap ms_own, ms_str, mt_own, mt_str;
-    if (!make_map(&ms_own, src, total_M, TC_BM) || !make_map(&ms_str, src, total_M, TC_BN) ||
-        !make_map(&mt_own, tgt, total_N, TC_BM) || !make_map(&mt_str, tgt, total_N, TC_BN)) return cudaErrorNotSupported;
+    if (!make_map(&ms_own, src_bf16, total_M, TC_BM) || !make_map(&ms_str, src_bf16, total_M, TC_BN) ||
+        !make_map(&mt_own, tgt_bf16, total_N, TC_BM) || !make_map(&mt_str, tgt_bf16, total_N, TC_BN)) return cudaErrorNotSupported;
     const size_t smem = sizeof(TcSmem) + 1024;
     static bool once = false;
     if (!once) {

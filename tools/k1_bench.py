@@ -37,4 +37,8 @@ for a, b in evs:
     L.bfr_debug_set_k1_events(vp(a.cuda_event), vp(b.cuda_event)); run()
 torch.cuda.synchronize()
 ms = min(a.elapsed_time(b) for a, b in evs)
+if hasattr(L, "bfr_dbg_counters"):
+    import numpy as np
+    out = np.zeros(8, dtype=np.uint64); L.bfr_dbg_counters(out.ctypes.data_as(vp))
+    print("dbg counters (8 launches x 2 dirs): compactions %d entries_in %d entries_out %d overflow_valid %d overflow_invalid %d" % tuple(out[:5]))
 print("%s P=%d N=%d: K1 %.3f ms  %.2f TFLOP/s  checksum %d" % (os.path.basename(so), P, N, ms, 2.0 * N * N * 32 * P / ms * 1e-9, int(nn_s.sum().item() % 1000003)))

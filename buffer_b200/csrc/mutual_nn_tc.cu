@@ -45,10 +45,20 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 #ifndef TC_EXP
 #define TC_EXP 0
 #endif
+#ifndef TC_POLL
+#define TC_POLL 0
+#endif
 constexpr int TC_SUB = 4;                       // candidate granularity: 4-column groups
 constexpr int TC_CAP = TC_CAP_N;                      // band events (32-column chunks with their 8 group maxima) kept per row
 constexpr int TC_GCAP = 32;                     // surviving 4-column groups per row handed to the exact re-check
 constexpr int TC_MAX_TILES = 48;                // streamed tiles per CTA (hn cache = 6144 floats)
+#ifndef TC_W_N
+#define TC_W_N 128
+#endif
+constexpr int TC_W = TC_W_N;                    // streamed columns per TMEM slot (one MMA N); a slot holds both row halves: 2 * TC_W TMEM columns
+constexpr int TC_NSLOT = 512 / (2 * TC_W);      // accumulator ring: the MMA warp runs up to TC_NSLOT slots ahead of the epilogue
+constexpr int TC_UPT = TC_BN / TC_W;            // slots ("units") per streamed tile
+static_assert(TC_W == 64 || TC_W == 128, "the epilogue pulls a whole slot (2 or 4 chunks of 32 columns) into registers");
 
 #ifdef TC_TIMING
 __device__ unsigned long long g_dbg[8];
@@ -58,15 +68,16 @@ struct TcSmem {
     uint16_t a[TC_BM * TC_D];                   // 16 KB bf16, SWIZZLE_64B K-major (one 64-byte row per descriptor); rows 128.. = second half
     uint16_t b[TC_STAGES][TC_BN * TC_D];        // 4 x 8 KB (after the last MMA: uint32_t glist[TC_GCAP][TC_BM], the groups to re-check)
     float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
-    float4 cmg[TC_EPI_WARPS][TC_CAP][2][32];    // band events [warp][slot][half][lane]: the eight 4-column group maxima of the chunk
-                                                // (once a warp has consumed its events: that warp's 8 KB staging area of the re-check)
-    uint2 cid[TC_EPI_WARPS][TC_CAP][32];        //   ... {chunk maximum (float bits), CTA-local first streamed column of the chunk}
+    struct Ev {                                 // band events of one epilogue warp (once consumed: the warp's 16 KB staging area of the re-check)
+        float4 cmg[TC_CAP][2][32];              //   [slot][half][lane]: the eight 4-column group maxima of the chunk
+        uint2 cid[TC_CAP][32];                  //   {chunk maximum (float bits), CTA-local first streamed column of the chunk}
+    } ev[TC_EPI_WARPS];
     float red[TC_THREADS / 32], red2[TC_THREADS / 32];
-    uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];
+    uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[TC_NSLOT], acc_empty[TC_NSLOT];
     uint32_t tmem_base;
 };
 static_assert(sizeof(uint16_t) * TC_STAGES * TC_BN * TC_D >= sizeof(uint32_t) * TC_GCAP * TC_BM, "group list must fit in the TMA ring");
-static_assert(TC_CAP * 2 * 32 * sizeof(float4) >= 2 * 256 * sizeof(float4), "a warp's event slice doubles as its 8 KB staging area");
+static_assert(sizeof(TcSmem::Ev) >= 4 * 256 * sizeof(float4), "a warp's event slice doubles as its 16 KB staging area (4 candidate columns x 32 rows x 128 B)");
 constexpr uint32_t TC_CMG_HALF = sizeof(float4) * 32;           // 512: second half of an event's group maxima
 constexpr uint32_t TC_CMG_SLOT = 2 * TC_CMG_HALF;               // 1024
 constexpr uint32_t TC_CID_SLOT = sizeof(uint2) * 32;            // 256
@@ -100,6 +111,14 @@ BFR_DEVINL void append_if_in_band(float c, float thr, uint32_t& p16, uint32_t& p
 }
 static_assert(TC_CMG_HALF == 512 && TC_CMG_SLOT == 1024 && TC_CID_SLOT == 256, "append_if_in_band hard-codes these strides");
 
+BFR_DEVINL void mbar_spin(uint64_t* bar, uint32_t parity)
+{   // busy poll (test_wait never suspends the thread)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SPIN_%=:\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra SPIN_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 BFR_DEVINL void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -193,7 +212,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* hn_str_p = hn_str + (size_t)p * pad_str;
 #ifdef TC_TIMING
-    long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq_wait = 0, tq_ld = 0, tq_proc = 0, tq_cmp = 0;
+    long long tv_glist = 0, tv_own = 0, tv_rounds = 0; long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq_wait = 0, tq_ld = 0, tq_proc = 0, tq_cmp = 0;
 #define TCT(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
 #else
 #define TCT(acc, stmt) { stmt; }
@@ -203,7 +222,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_init(&sm.a_full, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&sm.acc_full[a], 1); mbar_init(&sm.acc_empty[a], 4 * halves); }
+        for (int a = 0; a < TC_NSLOT; ++a) { mbar_init(&sm.acc_full[a], 1); mbar_init(&sm.acc_empty[a], 4 * halves); }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -239,6 +258,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(&sm.empty[s], ph ^ 1u);
+#ifdef TC_NOTMA
+                if (it >= TC_STAGES) { mbar_arrive(&sm.full[s]); continue; }
+#endif
                 mbar_expect_tx(&sm.full[s], TC_BN * TC_D * 2);
                 tma_load_2d(sm.b[s], &map_str, 0, os + (t_begin + it) * TC_BN, &sm.full[s]);
             }
@@ -246,26 +268,40 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 128, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = TC_W, M = 128
+#ifdef TC_N256HACK
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#else
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_W >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+#endif
             const uint64_t adesc0 = umma_desc_sw64(sm.a), adesc1 = umma_desc_sw64(sm.a + 128 * TC_D);
             mbar_wait(&sm.a_full, 0);
+            int u = 0;                                                // slot counter: unit u lives in ring slot u % TC_NSLOT
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
-                const int a = it & 1; const uint32_t aph = (uint32_t)(it >> 1) & 1u;
                 mbar_wait(&sm.full[s], ph);
-                mbar_wait(&sm.acc_empty[a], aph ^ 1u);
-                tc_fence_after();
-                const uint64_t bdesc = umma_desc_sw64(sm.b[s]);
-                for (int h = 0; h < halves; ++h) {
-                    const uint32_t d = tmem_base + (uint32_t)((a * 2 + h) * TC_BN);
-                    const uint64_t ad = h ? adesc1 : adesc0;
 #pragma unroll
-                    for (int k = 0; k < TC_MMAK; ++k)              // K = 16 per instruction: +32 bytes (2 x 16 B) per step inside the 64-byte row
-                        umma_bf16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+                for (int sub = 0; sub < TC_UPT; ++sub, ++u) {
+                    const int slot = u % TC_NSLOT; const uint32_t aph = (uint32_t)(u / TC_NSLOT) & 1u;
+#ifndef TC_NOWAIT
+                    mbar_wait(&sm.acc_empty[slot], aph ^ 1u);
+#endif
+                    tc_fence_after();
+                    const uint64_t bdesc = umma_desc_sw64(sm.b[s] + sub * TC_W * TC_D);     // TC_W rows further: a multiple of the 512-byte swizzle atom
+                    for (int h = 0; h < halves; ++h) {
+#ifdef TC_N256HACK
+                        const uint32_t d = tmem_base + (uint32_t)(h * 256);
+#else
+                        const uint32_t d = tmem_base + (uint32_t)(slot * 2 * TC_W + h * TC_W);
+#endif
+                        const uint64_t ad = h ? adesc1 : adesc0;
+#pragma unroll
+                        for (int k = 0; k < TC_MMAK; ++k)          // K = 16 per instruction: +32 bytes (2 x 16 B) per step inside the 64-byte row
+                            umma_bf16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&sm.acc_full[slot]);
                 }
-                umma_commit(&sm.empty[s]);
-                umma_commit(&sm.acc_full[a]);
+                umma_commit(&sm.empty[s]);                            // the stage is free once every MMA that reads it has completed
             }
         }
     } else if (warp - 2 < 4 * halves) {
@@ -282,10 +318,10 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         const bool uniform = hn_spread <= 0.0009765625f * str_max_sq;   // CTA-uniform (the branch below contains warp-collective TMEM loads)
         const float band = !valid ? -INFINITY : uniform ? two_eps + hn_spread : two_eps;     // rows beyond M never record an event
         float m_run = -INFINITY, dropped_max = -INFINITY;
-        const int ew = warp - 2;                                      // epilogue warp index: owns sm.cmg[ew] / sm.cid[ew]
-        const uint32_t p16_base = smem_u32(&sm.cmg[ew][0][0][lane]), p8_base = smem_u32(&sm.cid[ew][0][lane]);
+        const int ew = warp - 2;                                      // epilogue warp index: owns sm.ev[ew].cmg / sm.ev[ew].cid
+        const uint32_t p16_base = smem_u32(&sm.ev[ew].cmg[0][0][lane]), p8_base = smem_u32(&sm.ev[ew].cid[0][lane]);
         uint32_t p16 = p16_base, p8 = p8_base;                        // next free event slot of this row
-        const uint32_t p8_high = p8_base + (uint32_t)(TC_CAP - 4) * TC_CID_SLOT;   // a tile appends at most 4 events
+        const uint32_t p8_high = p8_base + (uint32_t)(TC_CAP - TC_W / 32) * TC_CID_SLOT;   // a unit appends at most TC_W / 32 events
 
         // one 32-column chunk: (add hn(b_j),) 4-column group maxima -> chunk maximum -> running maximum; if the chunk maximum is inside
         // the band the eight group maxima are kept as one event (predicated stores, no branch)
@@ -323,72 +359,70 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             const int cnt = (int)((p8 - p8_base) / TC_CID_SLOT);
             int n = 0;
             for (int k = 0; k < cnt; ++k) {
-                const uint2 e = sm.cid[ew][k][lane];
+                const uint2 e = sm.ev[ew].cid[k][lane];
                 if (__uint_as_float(e.x) >= thr) {
-                    if (n != k) { sm.cid[ew][n][lane] = e; sm.cmg[ew][n][0][lane] = sm.cmg[ew][k][0][lane]; sm.cmg[ew][n][1][lane] = sm.cmg[ew][k][1][lane]; }
+                    if (n != k) { sm.ev[ew].cid[n][lane] = e; sm.ev[ew].cmg[n][0][lane] = sm.ev[ew].cmg[k][0][lane]; sm.ev[ew].cmg[n][1][lane] = sm.ev[ew].cmg[k][1][lane]; }
                     ++n;
                 }
             }
 #ifdef TC_TIMING
             atomicAdd(&g_dbg[0], 1ull); atomicAdd(&g_dbg[1], (unsigned long long)cnt); atomicAdd(&g_dbg[2], (unsigned long long)n);
-            if (n > TC_CAP - 4) atomicAdd(&g_dbg[valid ? 3 : 4], 1ull);
+            if (n > TC_CAP - TC_W / 32) atomicAdd(&g_dbg[valid ? 3 : 4], 1ull);
 #endif
-            while (n > TC_CAP - 4) {
-                int jmin = 0; float cmin = __uint_as_float(sm.cid[ew][0][lane].x);
-                for (int k = 1; k < n; ++k) { const float ck = __uint_as_float(sm.cid[ew][k][lane].x); if (ck < cmin) { cmin = ck; jmin = k; } }
+            while (n > TC_CAP - TC_W / 32) {
+                int jmin = 0; float cmin = __uint_as_float(sm.ev[ew].cid[0][lane].x);
+                for (int k = 1; k < n; ++k) { const float ck = __uint_as_float(sm.ev[ew].cid[k][lane].x); if (ck < cmin) { cmin = ck; jmin = k; } }
                 dropped_max = fmaxf(dropped_max, cmin);
                 --n;
-                if (jmin != n) { sm.cid[ew][jmin][lane] = sm.cid[ew][n][lane]; sm.cmg[ew][jmin][0][lane] = sm.cmg[ew][n][0][lane]; sm.cmg[ew][jmin][1][lane] = sm.cmg[ew][n][1][lane]; }
+                if (jmin != n) { sm.ev[ew].cid[jmin][lane] = sm.ev[ew].cid[n][lane]; sm.ev[ew].cmg[jmin][0][lane] = sm.ev[ew].cmg[n][0][lane]; sm.ev[ew].cmg[jmin][1][lane] = sm.ev[ew].cmg[n][1][lane]; }
             }
             p16 = p16_base + (uint32_t)n * TC_CMG_SLOT; p8 = p8_base + (uint32_t)n * TC_CID_SLOT;
         };
-        // Software pipeline across tiles: while chunks (2,3) of tile `it` are reduced, chunks (0,1) of tile it+1 are already in flight, so the
-        // TMEM -> register latency never sits on the critical path of the two epilogue warps that share a scheduler.
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-        auto tile_addr = [&](int it) { return lane_base + (uint32_t)(((it & 1) * 2 + half) * TC_BN); };
-        auto acc_wait = [&](int it) {
+        // Accumulator ring: unit u = TC_W streamed columns (both row halves) lives in TMEM slot u % TC_NSLOT.  A warp pulls its 32 rows x 64
+        // columns into registers, hands the slot straight back to the MMA warp (the handshake + MMA latency round trip, ~800 cycles, is
+        // what has to be covered by the TC_NSLOT - 1 other slots) and only then reduces the two chunks.
+        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * TC_W);
+        const int nunits = ntiles * TC_UPT;
+        float va[32], vb[32];
+#if TC_W_N == 128
+        float vc[32], vd[32];
+#endif
+        for (int u = 0; u < nunits; ++u) {
+            const int slot = u % TC_NSLOT;
+            const uint32_t t0 = lane_base + (uint32_t)(slot * 2 * TC_W);
+            const int cb = u * TC_W;                                  // CTA-local first streamed column of this unit
+            const bool raw = uniform && t_begin * TC_BN + cb + TC_W <= N;    // no padding columns to mask and uniform norms
 #ifdef TC_TIMING
             const long long tw0 = clock64();
 #endif
-            mbar_wait(&sm.acc_full[it & 1], (uint32_t)(it >> 1) & 1u);
+#ifndef TC_NOWAIT
+            mbar_wait(&sm.acc_full[slot], (uint32_t)(u / TC_NSLOT) & 1u);
+#endif
 #ifdef TC_TIMING
             tq_wait += clock64() - tw0;
 #endif
             tc_fence_after();
             __syncwarp();
-        };
-        float va[32], vb[32], vc[32], vd[32];
-        acc_wait(0);
-        tmem_ld32_issue(tile_addr(0), va); tmem_ld32_issue(tile_addr(0) + 32, vb);
-        for (int it = 0; it < ntiles; ++it) {
-            const uint32_t t0 = tile_addr(it);
-            const int cb = it * TC_BN;                                // CTA-local streamed column of this tile
-            const bool raw = uniform && (t_begin + it + 1) * TC_BN <= N;   // full tile (no padding columns to mask) and uniform norms
-            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb));
+            tmem_ld32_issue(t0, va); tmem_ld32_issue(t0 + 32, vb);
+#if TC_W_N == 128
             tmem_ld32_issue(t0 + 64, vc); tmem_ld32_issue(t0 + 96, vd);
+            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb); tmem_ld_pin(vc); tmem_ld_pin(vd));
+#else
+            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb));
+#endif
+            tc_fence_before();                                        // all TMEM reads of this slot are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[slot]);
+#if TC_W_N == 128
+            TCT(tq_proc,
+            if (raw) { process(va, cb, std::true_type{}); process(vb, cb + 32, std::true_type{}); process(vc, cb + 64, std::true_type{}); process(vd, cb + 96, std::true_type{}); }
+            else { process(va, cb, std::false_type{}); process(vb, cb + 32, std::false_type{}); process(vc, cb + 64, std::false_type{}); process(vd, cb + 96, std::false_type{}); })
+#else
             TCT(tq_proc,
             if (raw) { process(va, cb, std::true_type{}); process(vb, cb + 32, std::true_type{}); }
             else { process(va, cb, std::false_type{}); process(vb, cb + 32, std::false_type{}); })
-            TCT(tq_ld, tmem_ld_wait(vc); tmem_ld_pin(vd));
-            tc_fence_before();                                        // all TMEM reads of this accumulator are complete
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.acc_empty[it & 1]);        // the MMA warp may overwrite it while the last chunks are reduced
-            if (it + 1 < ntiles) {
-                acc_wait(it + 1);
-                tmem_ld32_issue(tile_addr(it + 1), va); tmem_ld32_issue(tile_addr(it + 1) + 32, vb);
-            }
-            TCT(tq_proc,
-            if (raw) { process(vc, cb + 64, std::true_type{}); process(vd, cb + 96, std::true_type{}); }
-            else { process(vc, cb + 64, std::false_type{}); process(vd, cb + 96, std::false_type{}); })
-#if TC_EXP == 10
-            if (p8 > p8_high) { p16 = p16_base; p8 = p8_base; }
-#else
-#if TC_EXP == 12
-            if (p8 > p8_high) { if (ntiles > 100000) compact(); else { p16 = p16_base; p8 = p8_base; } }
-#else
+#endif
             TCT(tq_cmp, if (p8 > p8_high) compact());
-#endif
-#endif
         }
 
 #ifdef TC_TIMING
@@ -397,32 +431,13 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         // ---- exact FP32 re-check of the surviving groups (or of the whole row after an overflow) ---------------------------
         // One lane = one row, but the candidate rows are fetched cooperatively: 8 lanes read the 8 float4 of one 128-byte row
         // (coalesced, 4 rows per warp-wide load) and transpose through an XOR-swizzled per-warp staging area (the warp's own event
-        // slice, dead once the group list is built), so that the L1 sees 4 wavefronts per load instruction instead of 32.
+        // slice, dead once the group list is built), so that the L1 sees 4 wavefronts per load instruction instead of 32.  The four
+        // columns of a group are fetched together (one memory round trip per group, usually one per row).
         {
             const float thr = m_run - band;
             bool overflow = dropped_max >= thr;                       // a dropped event could still hold the maximum: exact scan of the row
             const int j_end = min(N, t_end * TC_BN);
             float best = -INFINITY; int best_j = 0x7fffffff;
-            // surviving events -> list of in-band 4-column groups (global streamed column of each), in the idle TMA ring
-            uint32_t (*glist)[TC_BM] = reinterpret_cast<uint32_t (*)[TC_BM]>(&sm.b[0][0]);
-            int n = 0;
-            if (valid && !overflow && TC_EXP != 10 && TC_EXP != 11 && TC_EXP != 12) {
-                const int cnt = (int)((p8 - p8_base) / TC_CID_SLOT);
-                for (int k = 0; k < cnt && !overflow; ++k) {
-                    const uint2 e = sm.cid[ew][k][lane];
-                    if (__uint_as_float(e.x) < thr) continue;
-                    const float4 g0 = sm.cmg[ew][k][0][lane], g1 = sm.cmg[ew][k][1][lane];
-                    const float mg[8] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w };
-#pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (mg[g] >= thr) {
-                            if (n < TC_GCAP) glist[n++][r] = (uint32_t)(t_begin * TC_BN) + e.y + 4u * (uint32_t)g; else overflow = true;
-                        }
-                }
-                if (overflow) n = 0;
-            }
-            __syncwarp();                                             // every lane is done with its events: the slice becomes the staging area
-            float4* stage = &sm.cmg[ew][0][0][0];                     // 2 buffers x (32 rows x 8 float4)
             const int sub = lane >> 3, chunk = lane & 7;
             // gather 32 rows (one per lane, row index `want`, -1 = none) of `base` into registers, 4 rows per instruction
             auto fetch = [&](const float* __restrict__ base, int want, float4 (&reg)[8]) {
@@ -433,48 +448,73 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                     reg[s8] = (jr >= 0) ? __ldg(reinterpret_cast<const float4*>(base + (size_t)jr * TC_D) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             };
-            auto put = [&](int buf, const float4 (&reg)[8]) {
+            float4 reg[TC_SUB][8];
+            fetch(x_own + (size_t)oo * TC_D, valid ? row : -1, reg[0]);      // own row: in flight while the events are decoded
+            // surviving events -> list of in-band 4-column groups (global streamed column of each), in the idle TMA ring
+            uint32_t (*glist)[TC_BM] = reinterpret_cast<uint32_t (*)[TC_BM]>(&sm.b[0][0]);
+            int n = 0;
+            if (valid && !overflow && TC_EXP != 10 && TC_EXP != 11 && TC_EXP != 12) {
+                const int cnt = (int)((p8 - p8_base) / TC_CID_SLOT);
+                for (int k = 0; k < cnt; ++k) {
+                    const uint2 e = sm.ev[ew].cid[k][lane];
+                    if (__uint_as_float(e.x) < thr) continue;
+                    const float4 g0 = sm.ev[ew].cmg[k][0][lane], g1 = sm.ev[ew].cmg[k][1][lane];
+                    const float mg[8] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w };
+                    const uint32_t colbase = (uint32_t)(t_begin * TC_BN) + e.y;
 #pragma unroll
-                for (int s8 = 0; s8 < 8; ++s8) { const int rid = 4 * s8 + sub; stage[buf * 256 + rid * 8 + (chunk ^ (rid & 7))] = reg[s8]; }
+                    for (int g = 0; g < 8; ++g)
+                        if (mg[g] >= thr) { if (n < TC_GCAP) glist[n][r] = colbase + 4u * (uint32_t)g; ++n; }
+                }
+                if (n > TC_GCAP) { overflow = true; n = 0; }
+            }
+#ifdef TC_TIMING
+            tv_glist = clock64();
+#endif
+            __syncwarp();                                             // every lane is done with its events: the slice becomes the staging area
+            float4* stage = reinterpret_cast<float4*>(&sm.ev[ew]);    // TC_SUB buffers x (32 rows x 8 float4)
+            auto put = [&](int buf, const float4 (&rg)[8]) {
+#pragma unroll
+                for (int s8 = 0; s8 < 8; ++s8) { const int rid = 4 * s8 + sub; stage[buf * 256 + rid * 8 + (chunk ^ (rid & 7))] = rg[s8]; }
             };
             auto get = [&](int buf, float4 (&rowv)[8]) {
 #pragma unroll
                 for (int c = 0; c < 8; ++c) rowv[c] = stage[buf * 256 + lane * 8 + (c ^ (lane & 7))];
             };
-            float4 own[8], reg[8];
-            fetch(x_own + (size_t)oo * TC_D, valid ? row : -1, reg);
-            put(0, reg);
+            float4 own[8];
+            put(0, reg[0]);
             __syncwarp();
             get(0, own);
             __syncwarp();
             const int nmax = __reduce_max_sync(0xffffffffu, n);
+#ifdef TC_TIMING
+            tv_own = clock64(); tv_rounds = nmax;
+#endif
             const float* xs = x_str + (size_t)os * TC_D;
-            auto column = [&](int k, int u) {                         // streamed column this lane evaluates in sub-round (k, u), or -1
-                if (k >= n) return -1;
-                const int j = (int)glist[k][r] + u;
-                return j < j_end ? j : -1;
-            };
-            const int rounds = nmax * TC_SUB;
-            if (rounds > 0) { fetch(xs, column(0, 0), reg); put(0, reg); }
-            for (int it = 0; it < rounds; ++it) {
-                const int j = column(it / TC_SUB, it % TC_SUB);
-                const bool more = it + 1 < rounds;
-                if (more) fetch(xs, column((it + 1) / TC_SUB, (it + 1) % TC_SUB), reg);     // next sub-round's loads in flight
-                __syncwarp();
-                if (j >= 0) {
-                    float4 c[8];
-                    get(it & 1, c);
-                    const float cand_hn = sm.hn[j - t_begin * TC_BN];
-                    float acc = COLDIR ? own_hn : cand_hn;
+            for (int k = 0; k < nmax; ++k) {
+                const int j0 = (k < n) ? (int)glist[k][r] : -0x40000000;     // first column of this lane's k-th group
+                int jc[TC_SUB];
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; ++k4) {
-                        acc = __fmaf_rn(own[k4].x, c[k4].x, acc); acc = __fmaf_rn(own[k4].y, c[k4].y, acc);
-                        acc = __fmaf_rn(own[k4].z, c[k4].z, acc); acc = __fmaf_rn(own[k4].w, c[k4].w, acc);
+                for (int u = 0; u < TC_SUB; ++u) { jc[u] = (j0 >= 0 && j0 + u < j_end) ? j0 + u : -1; fetch(xs, jc[u], reg[u]); }
+#pragma unroll
+                for (int u = 0; u < TC_SUB; ++u) put(u, reg[u]);
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < TC_SUB; ++u) {
+                    if (jc[u] >= 0) {
+                        float4 c[8];
+                        get(u, c);
+                        const float cand_hn = sm.hn[jc[u] - t_begin * TC_BN];
+                        float acc = COLDIR ? own_hn : cand_hn;
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; ++k4) {
+                            acc = __fmaf_rn(own[k4].x, c[k4].x, acc); acc = __fmaf_rn(own[k4].y, c[k4].y, acc);
+                            acc = __fmaf_rn(own[k4].z, c[k4].z, acc); acc = __fmaf_rn(own[k4].w, c[k4].w, acc);
+                        }
+                        const float e = COLDIR ? __fadd_rn(acc, cand_hn) : acc;
+                        if (e > best || (e == best && jc[u] < best_j)) { best = e; best_j = jc[u]; }
                     }
-                    const float e = COLDIR ? __fadd_rn(acc, cand_hn) : acc;
-                    if (e > best || (e == best && j < best_j)) { best = e; best_j = j; }
                 }
-                if (more) put((it + 1) & 1, reg);
+                __syncwarp();
             }
             if (valid && overflow) {                                  // pathological row (many near-duplicates): exact scan
                 for (int j = t_begin * TC_BN; j < j_end; ++j) {
@@ -494,7 +534,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     __syncthreads();
 #ifdef TC_TIMING
     tq4 = clock64();
-    if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && (warp == 2 || warp == 9)) printf("cta %d warp %d: setup %lld main %lld (acc wait %lld ldwait %lld proc %lld compact %lld) verify %lld tailwait %lld\n", blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq_wait, tq_ld, tq_proc, tq_cmp, tq3 - tq2, tq4 - tq3);
+    if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && (warp == 2 || warp == 9)) printf("cta %d warp %d: setup %lld main %lld (acc wait %lld ldwait %lld proc %lld compact %lld) verify %lld (glist %lld own %lld nmax %lld) tailwait %lld\n", blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq_wait, tq_ld, tq_proc, tq_cmp, tq3 - tq2, tv_glist - tq2, tv_own - tv_glist, tv_rounds, tq4 - tq3);
 #endif
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }

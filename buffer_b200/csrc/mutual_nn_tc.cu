@@ -28,16 +28,16 @@
 namespace bfr {
 
 constexpr int TC_BM = 256;                      // own rows per CTA = two M=128 accumulator halves sharing every streamed tile
-constexpr int TC_BN = 128;                      // streamed rows per tile (MMA N)
+constexpr int TC_BN = 256;                      // streamed rows per tile = MMA N (the largest cta_group::1 shape: see the note on accumulator switches below)
 constexpr int TC_D = 32;
 #ifndef TC_MMAK
 #define TC_MMAK (TC_D / 16)
 #endif
 #ifndef TC_STAGES_N
-#define TC_STAGES_N 4
+#define TC_STAGES_N 3
 #endif
 #ifndef TC_CAP_N
-#define TC_CAP_N 14
+#define TC_CAP_N 13
 #endif
 constexpr int TC_STAGES = TC_STAGES_N;
 constexpr int TC_EPI_WARPS = 8;                 // one epilogue thread per own row
@@ -51,14 +51,7 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_SUB = 4;                       // candidate granularity: 4-column groups
 constexpr int TC_CAP = TC_CAP_N;                      // band events (32-column chunks with their 8 group maxima) kept per row
 constexpr int TC_GCAP = 32;                     // surviving 4-column groups per row handed to the exact re-check
-constexpr int TC_MAX_TILES = 48;                // streamed tiles per CTA (hn cache = 6144 floats)
-#ifndef TC_W_N
-#define TC_W_N 128
-#endif
-constexpr int TC_W = TC_W_N;                    // streamed columns per TMEM slot (one MMA N); a slot holds both row halves: 2 * TC_W TMEM columns
-constexpr int TC_NSLOT = 512 / (2 * TC_W);      // accumulator ring: the MMA warp runs up to TC_NSLOT slots ahead of the epilogue
-constexpr int TC_UPT = TC_BN / TC_W;            // slots ("units") per streamed tile
-static_assert(TC_W == 64 || TC_W == 128, "the epilogue pulls a whole slot (2 or 4 chunks of 32 columns) into registers");
+constexpr int TC_MAX_TILES = 24;                // streamed tiles per CTA (hn cache = 6144 floats)
 
 #ifdef TC_TIMING
 __device__ unsigned long long g_dbg[8];
@@ -66,14 +59,14 @@ __device__ unsigned long long g_dbg[8];
 
 struct TcSmem {
     uint16_t a[TC_BM * TC_D];                   // 16 KB bf16, SWIZZLE_64B K-major (one 64-byte row per descriptor); rows 128.. = second half
-    uint16_t b[TC_STAGES][TC_BN * TC_D];        // 4 x 8 KB (after the last MMA: uint32_t glist[TC_GCAP][TC_BM], the groups to re-check)
+    uint16_t b[TC_STAGES][TC_BN * TC_D];        // 3 x 16 KB (after the last MMA: uint32_t glist[TC_GCAP][TC_BM], the groups to re-check)
     float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
     struct Ev {                                 // band events of one epilogue warp (once consumed: the warp's 16 KB staging area of the re-check)
         float4 cmg[TC_CAP][2][32];              //   [slot][half][lane]: the eight 4-column group maxima of the chunk
         uint2 cid[TC_CAP][32];                  //   {chunk maximum (float bits), CTA-local first streamed column of the chunk}
     } ev[TC_EPI_WARPS];
     float red[TC_THREADS / 32], red2[TC_THREADS / 32];
-    uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[TC_NSLOT], acc_empty[TC_NSLOT];
+    uint64_t a_full, full[TC_STAGES], empty[TC_STAGES], acc_full[2], acc_empty[2];     // acc_*[h]: the accumulator tile of row half h
     uint32_t tmem_base;
 };
 static_assert(sizeof(uint16_t) * TC_STAGES * TC_BN * TC_D >= sizeof(uint32_t) * TC_GCAP * TC_BM, "group list must fit in the TMA ring");
@@ -212,7 +205,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* hn_str_p = hn_str + (size_t)p * pad_str;
 #ifdef TC_TIMING
-    long long tv_glist = 0, tv_own = 0, tv_rounds = 0; long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq_wait = 0, tq_ld = 0, tq_proc = 0, tq_cmp = 0;
+    long long tv_glist = 0, tv_own = 0, tv_rounds = 0, tv_lat = 0; long long tq0 = clock64(), tq1 = 0, tq2 = 0, tq3 = 0, tq4 = 0, tq_wait = 0, tq_ld = 0, tq_proc = 0, tq_cmp = 0;
 #define TCT(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
 #else
 #define TCT(acc, stmt) { stmt; }
@@ -222,7 +215,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     if (threadIdx.x == 0) {
         mbar_init(&sm.a_full, 1);
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], 1); }
-        for (int a = 0; a < TC_NSLOT; ++a) { mbar_init(&sm.acc_full[a], 1); mbar_init(&sm.acc_empty[a], 4 * halves); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&sm.acc_full[a], 1); mbar_init(&sm.acc_empty[a], 4); }
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -268,38 +261,25 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = TC_W, M = 128
-#ifdef TC_N256HACK
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-#else
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_W >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-#endif
+            // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 256, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint64_t adesc0 = umma_desc_sw64(sm.a), adesc1 = umma_desc_sw64(sm.a + 128 * TC_D);
             mbar_wait(&sm.a_full, 0);
-            int u = 0;                                                // slot counter: unit u lives in ring slot u % TC_NSLOT
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(&sm.full[s], ph);
-#pragma unroll
-                for (int sub = 0; sub < TC_UPT; ++sub, ++u) {
-                    const int slot = u % TC_NSLOT; const uint32_t aph = (uint32_t)(u / TC_NSLOT) & 1u;
+                const uint64_t bdesc = umma_desc_sw64(sm.b[s]);
+                for (int h = 0; h < halves; ++h) {                    // one accumulator tile (128 rows x 256 streamed columns) per row half
 #ifndef TC_NOWAIT
-                    mbar_wait(&sm.acc_empty[slot], aph ^ 1u);
+                    mbar_wait(&sm.acc_empty[h], ((uint32_t)it & 1u) ^ 1u);
 #endif
                     tc_fence_after();
-                    const uint64_t bdesc = umma_desc_sw64(sm.b[s] + sub * TC_W * TC_D);     // TC_W rows further: a multiple of the 512-byte swizzle atom
-                    for (int h = 0; h < halves; ++h) {
-#ifdef TC_N256HACK
-                        const uint32_t d = tmem_base + (uint32_t)(h * 256);
-#else
-                        const uint32_t d = tmem_base + (uint32_t)(slot * 2 * TC_W + h * TC_W);
-#endif
-                        const uint64_t ad = h ? adesc1 : adesc0;
+                    const uint32_t d = tmem_base + (uint32_t)(h * TC_BN);
+                    const uint64_t ad = h ? adesc1 : adesc0;
 #pragma unroll
-                        for (int k = 0; k < TC_MMAK; ++k)          // K = 16 per instruction: +32 bytes (2 x 16 B) per step inside the 64-byte row
-                            umma_bf16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
-                    }
-                    umma_commit(&sm.acc_full[slot]);
+                    for (int k = 0; k < TC_MMAK; ++k)              // K = 16 per instruction: +32 bytes (2 x 16 B) per step inside the 64-byte row
+                        umma_bf16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+                    umma_commit(&sm.acc_full[h]);
                 }
                 umma_commit(&sm.empty[s]);                            // the stage is free once every MMA that reads it has completed
             }
@@ -321,11 +301,10 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         const int ew = warp - 2;                                      // epilogue warp index: owns sm.ev[ew].cmg / sm.ev[ew].cid
         const uint32_t p16_base = smem_u32(&sm.ev[ew].cmg[0][0][lane]), p8_base = smem_u32(&sm.ev[ew].cid[0][lane]);
         uint32_t p16 = p16_base, p8 = p8_base;                        // next free event slot of this row
-        const uint32_t p8_high = p8_base + (uint32_t)(TC_CAP - TC_W / 32) * TC_CID_SLOT;   // a unit appends at most TC_W / 32 events
+        const uint32_t p8_high = p8_base + (uint32_t)(TC_CAP - 4) * TC_CID_SLOT;   // a batch of 128 columns appends at most 4 events
 
-        // one 32-column chunk: (add hn(b_j),) 4-column group maxima -> chunk maximum -> running maximum; if the chunk maximum is inside
-        // the band the eight group maxima are kept as one event (predicated stores, no branch)
-        auto process = [&](float (&v)[32], int colbase, auto raw_tag) {
+        // one 32-column chunk: (add hn(b_j),) 4-column group maxima -> chunk maximum
+        auto reduce_chunk = [&](float (&v)[32], int colbase, float (&mg)[8], auto raw_tag) -> float {
             constexpr bool RAW = decltype(raw_tag)::value;            // RAW: v stays the bare dot product, compared in "dot + hmax" units
             if (!RAW) {
 #pragma unroll
@@ -335,21 +314,32 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                     unpack2(lo, v[4 * c4], v[4 * c4 + 1]); unpack2(hi, v[4 * c4 + 2], v[4 * c4 + 3]);
                 }
             }
-#if TC_EXP == 7
-            m_run = fmaxf(m_run, v[0] + v[31]); return;
-#endif
-            float mg[8];                                              // maxima of the eight 4-column groups, in raw dot-product units
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < 8; ++k) {                             // maxima of the eight 4-column groups, in raw dot-product units
                 mg[k] = fmaxf(max3(v[4 * k], v[4 * k + 1], v[4 * k + 2]), v[4 * k + 3]);
                 if (!RAW) mg[k] -= hmax;                              // hn-adjusted tiles: shift so that both kinds of tile compare
             }
-            const float c = fmaxf(max3(max3(mg[0], mg[1], mg[2]), mg[3], mg[4]), max3(mg[5], mg[6], mg[7]));
-            m_run = fmaxf(m_run, c);
+            return fmaxf(max3(max3(mg[0], mg[1], mg[2]), mg[3], mg[4]), max3(mg[5], mg[6], mg[7]));
+        };
+        // one batch of four chunks (128 streamed columns): the four reductions are independent; the running maximum is raised by the
+        // whole batch first, so all four chunks are tested against one (tighter) threshold; a chunk whose maximum is inside the band
+        // keeps its eight group maxima as one event (predicated stores, no branch)
+        auto process_batch = [&](float (&v0)[32], float (&v1)[32], float (&v2)[32], float (&v3)[32], int colbase, auto raw_tag) {
+#if TC_EXP == 7
+            m_run = fmaxf(m_run, (v0[0] + v1[31]) + (v2[0] + v3[31])); return;
+#endif
+            float g0[8], g1[8], g2[8], g3[8];
+            const float c0 = reduce_chunk(v0, colbase, g0, raw_tag), c1 = reduce_chunk(v1, colbase + 32, g1, raw_tag);
+            const float c2 = reduce_chunk(v2, colbase + 64, g2, raw_tag), c3 = reduce_chunk(v3, colbase + 96, g3, raw_tag);
+            m_run = fmaxf(max3(m_run, c0, c1), fmaxf(c2, c3));
 #if TC_EXP == 8
             return;
 #endif
-            append_if_in_band(c, m_run - band, p16, p8, mg, (uint32_t)colbase);
+            const float thr = m_run - band;
+            append_if_in_band(c0, thr, p16, p8, g0, (uint32_t)colbase);
+            append_if_in_band(c1, thr, p16, p8, g1, (uint32_t)(colbase + 32));
+            append_if_in_band(c2, thr, p16, p8, g2, (uint32_t)(colbase + 64));
+            append_if_in_band(c3, thr, p16, p8, g3, (uint32_t)(colbase + 96));
         };
         // rare (per lane, once the slots run low): drop the events that fell out of the band.  If more than TC_CAP - 4 survive (the running
         // maximum is still creeping up through typical chunk maxima) the lowest ones are dropped too and their maximum remembered: the row
@@ -367,9 +357,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             }
 #ifdef TC_TIMING
             atomicAdd(&g_dbg[0], 1ull); atomicAdd(&g_dbg[1], (unsigned long long)cnt); atomicAdd(&g_dbg[2], (unsigned long long)n);
-            if (n > TC_CAP - TC_W / 32) atomicAdd(&g_dbg[valid ? 3 : 4], 1ull);
+            if (n > TC_CAP - 4) atomicAdd(&g_dbg[valid ? 3 : 4], 1ull);
 #endif
-            while (n > TC_CAP - TC_W / 32) {
+            while (n > TC_CAP - 4) {
                 int jmin = 0; float cmin = __uint_as_float(sm.ev[ew].cid[0][lane].x);
                 for (int k = 1; k < n; ++k) { const float ck = __uint_as_float(sm.ev[ew].cid[k][lane].x); if (ck < cmin) { cmin = ck; jmin = k; } }
                 dropped_max = fmaxf(dropped_max, cmin);
@@ -378,51 +368,43 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             }
             p16 = p16_base + (uint32_t)n * TC_CMG_SLOT; p8 = p8_base + (uint32_t)n * TC_CID_SLOT;
         };
-        // Accumulator ring: unit u = TC_W streamed columns (both row halves) lives in TMEM slot u % TC_NSLOT.  A warp pulls its 32 rows x 64
-        // columns into registers, hands the slot straight back to the MMA warp (the handshake + MMA latency round trip, ~800 cycles, is
-        // what has to be covered by the TC_NSLOT - 1 other slots) and only then reduces the two chunks.
-        const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * TC_W);
-        const int nunits = ntiles * TC_UPT;
-        float va[32], vb[32];
-#if TC_W_N == 128
-        float vc[32], vd[32];
-#endif
-        for (int u = 0; u < nunits; ++u) {
-            const int slot = u % TC_NSLOT;
-            const uint32_t t0 = lane_base + (uint32_t)(slot * 2 * TC_W);
-            const int cb = u * TC_W;                                  // CTA-local first streamed column of this unit
-            const bool raw = uniform && t_begin * TC_BN + cb + TC_W <= N;    // no padding columns to mask and uniform norms
+        // The tensor pipe only streams back-to-back MMAs that accumulate into the SAME tile; every switch to another accumulator tile
+        // drains it (~350 cycles, independent of N: tools/microbench/mma_bubble.cu).  With K = 32 there are just two MMAs per tile, so
+        // the tile is made as large as the instruction allows (128 x 256) and each row half owns ONE such tile (2 x 256 = all 512 TMEM
+        // columns).  The halves alternate: while the four warps of one half pull their tile into registers and reduce it, the tensor
+        // core fills the tile of the other half.  A warp hands its tile back as soon as the last 128 columns are in registers.
+        const uint32_t t0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * TC_BN);
+        float va[32], vb[32], vc[32], vd[32];
+        for (int it = 0; it < ntiles; ++it) {
+            const int cb = it * TC_BN;                                // CTA-local first streamed column of this tile
 #ifdef TC_TIMING
             const long long tw0 = clock64();
 #endif
 #ifndef TC_NOWAIT
-            mbar_wait(&sm.acc_full[slot], (uint32_t)(u / TC_NSLOT) & 1u);
+            mbar_wait(&sm.acc_full[half], (uint32_t)it & 1u);
 #endif
 #ifdef TC_TIMING
             tq_wait += clock64() - tw0;
 #endif
             tc_fence_after();
             __syncwarp();
-            tmem_ld32_issue(t0, va); tmem_ld32_issue(t0 + 32, vb);
-#if TC_W_N == 128
-            tmem_ld32_issue(t0 + 64, vc); tmem_ld32_issue(t0 + 96, vd);
-            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb); tmem_ld_pin(vc); tmem_ld_pin(vd));
-#else
-            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb));
-#endif
-            tc_fence_before();                                        // all TMEM reads of this slot are complete
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.acc_empty[slot]);
-#if TC_W_N == 128
-            TCT(tq_proc,
-            if (raw) { process(va, cb, std::true_type{}); process(vb, cb + 32, std::true_type{}); process(vc, cb + 64, std::true_type{}); process(vd, cb + 96, std::true_type{}); }
-            else { process(va, cb, std::false_type{}); process(vb, cb + 32, std::false_type{}); process(vc, cb + 64, std::false_type{}); process(vd, cb + 96, std::false_type{}); })
-#else
-            TCT(tq_proc,
-            if (raw) { process(va, cb, std::true_type{}); process(vb, cb + 32, std::true_type{}); }
-            else { process(va, cb, std::false_type{}); process(vb, cb + 32, std::false_type{}); })
-#endif
-            TCT(tq_cmp, if (p8 > p8_high) compact());
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {                          // two batches of 128 columns
+                const int cbb = cb + b2 * 128;
+                const bool raw = uniform && t_begin * TC_BN + cbb + 128 <= N;    // no padding columns to mask and uniform norms
+                tmem_ld32_issue(t0 + b2 * 128, va); tmem_ld32_issue(t0 + b2 * 128 + 32, vb);
+                tmem_ld32_issue(t0 + b2 * 128 + 64, vc); tmem_ld32_issue(t0 + b2 * 128 + 96, vd);
+                TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb); tmem_ld_pin(vc); tmem_ld_pin(vd));
+                if (b2 == 1) {
+                    tc_fence_before();                                // all TMEM reads of this tile are complete
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.acc_empty[half]);
+                }
+                TCT(tq_proc,
+                if (raw) process_batch(va, vb, vc, vd, cbb, std::true_type{});
+                else process_batch(va, vb, vc, vd, cbb, std::false_type{});)
+                TCT(tq_cmp, if (p8 > p8_high) compact());
+            }
         }
 
 #ifdef TC_TIMING
@@ -455,15 +437,21 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             int n = 0;
             if (valid && !overflow && TC_EXP != 10 && TC_EXP != 11 && TC_EXP != 12) {
                 const int cnt = (int)((p8 - p8_base) / TC_CID_SLOT);
-                for (int k = 0; k < cnt; ++k) {
-                    const uint2 e = sm.ev[ew].cid[k][lane];
-                    if (__uint_as_float(e.x) < thr) continue;
-                    const float4 g0 = sm.ev[ew].cmg[k][0][lane], g1 = sm.ev[ew].cmg[k][1][lane];
-                    const float mg[8] = { g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w };
-                    const uint32_t colbase = (uint32_t)(t_begin * TC_BN) + e.y;
+                uint32_t q_ev = 0;                                    // events whose chunk maximum is still inside the band
 #pragma unroll
-                    for (int g = 0; g < 8; ++g)
-                        if (mg[g] >= thr) { if (n < TC_GCAP) glist[n][r] = colbase + 4u * (uint32_t)g; ++n; }
+                for (int k = 0; k < TC_CAP; ++k)
+                    if (k < cnt && __uint_as_float(sm.ev[ew].cid[k][lane].x) >= thr) q_ev |= 1u << k;
+                while (q_ev) {                                        // lanes walk their own (few) events in lock step
+                    const int k = __ffs((int)q_ev) - 1; q_ev &= q_ev - 1;
+                    const float4 g0 = sm.ev[ew].cmg[k][0][lane], g1 = sm.ev[ew].cmg[k][1][lane];
+                    const uint32_t colbase = (uint32_t)(t_begin * TC_BN) + sm.ev[ew].cid[k][lane].y;
+                    uint32_t q_g = (g0.x >= thr ? 1u : 0u) | (g0.y >= thr ? 2u : 0u) | (g0.z >= thr ? 4u : 0u) | (g0.w >= thr ? 8u : 0u) |
+                                   (g1.x >= thr ? 16u : 0u) | (g1.y >= thr ? 32u : 0u) | (g1.z >= thr ? 64u : 0u) | (g1.w >= thr ? 128u : 0u);
+                    while (q_g) {
+                        const int g = __ffs((int)q_g) - 1; q_g &= q_g - 1;
+                        if (n < TC_GCAP) glist[n][r] = colbase + 4u * (uint32_t)g;
+                        ++n;
+                    }
                 }
                 if (n > TC_GCAP) { overflow = true; n = 0; }
             }
@@ -495,9 +483,15 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                 int jc[TC_SUB];
 #pragma unroll
                 for (int u = 0; u < TC_SUB; ++u) { jc[u] = (j0 >= 0 && j0 + u < j_end) ? j0 + u : -1; fetch(xs, jc[u], reg[u]); }
+#ifdef TC_TIMING
+                const long long tr0 = clock64();
+#endif
 #pragma unroll
                 for (int u = 0; u < TC_SUB; ++u) put(u, reg[u]);
                 __syncwarp();
+#ifdef TC_TIMING
+                tv_lat += clock64() - tr0;
+#endif
 #pragma unroll
                 for (int u = 0; u < TC_SUB; ++u) {
                     if (jc[u] >= 0) {
@@ -534,7 +528,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     __syncthreads();
 #ifdef TC_TIMING
     tq4 = clock64();
-    if (blockIdx.z == 3 && blockIdx.x < 2 && lane == 0 && (warp == 2 || warp == 9)) printf("cta %d warp %d: setup %lld main %lld (acc wait %lld ldwait %lld proc %lld compact %lld) verify %lld (glist %lld own %lld nmax %lld) tailwait %lld\n", blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq_wait, tq_ld, tq_proc, tq_cmp, tq3 - tq2, tv_glist - tq2, tv_own - tv_glist, tv_rounds, tq4 - tq3);
+    if (blockIdx.z == 3 && blockIdx.x == 1 && lane == 0 && (warp == 2 || warp == 9)) printf("dir %d cta %d warp %d: setup %lld main %lld (acc wait %lld ldwait %lld proc %lld compact %lld) verify %lld (glist %lld own %lld nmax %lld loadwait %lld) tailwait %lld\n", (int)COLDIR, blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq_wait, tq_ld, tq_proc, tq_cmp, tq3 - tq2, tv_glist - tq2, tv_own - tv_glist, tv_rounds, tv_lat, tq4 - tq3);
 #endif
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }

@@ -321,18 +321,20 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             }
             return fmaxf(max3(max3(mg[0], mg[1], mg[2]), mg[3], mg[4]), max3(mg[5], mg[6], mg[7]));
         };
-        // one batch of four chunks (128 streamed columns): the four reductions are independent; the running maximum is raised by the
-        // whole batch first, so all four chunks are tested against one (tighter) threshold; a chunk whose maximum is inside the band
-        // keeps its eight group maxima as one event (predicated stores, no branch)
-        auto process_batch = [&](float (&v0)[32], float (&v1)[32], float (&v2)[32], float (&v3)[32], int colbase, auto raw_tag) {
+        // one batch of four chunks (128 streamed columns), in two steps so that the next TMEM load can be issued in between: the four
+        // reductions are independent; the running maximum is raised by the whole batch first, so all four chunks are tested against one
+        // (tighter) threshold; a chunk whose maximum is inside the band keeps its eight group maxima as one event (predicated stores)
+        float g0[8], g1[8], g2[8], g3[8], c0, c1, c2, c3;
+        auto reduce_batch = [&](float (&v0)[32], float (&v1)[32], float (&v2)[32], float (&v3)[32], int colbase, auto raw_tag) {
 #if TC_EXP == 7
-            m_run = fmaxf(m_run, (v0[0] + v1[31]) + (v2[0] + v3[31])); return;
+            c0 = (v0[0] + v1[31]) + (v2[0] + v3[31]); c1 = c2 = c3 = c0; return;
 #endif
-            float g0[8], g1[8], g2[8], g3[8];
-            const float c0 = reduce_chunk(v0, colbase, g0, raw_tag), c1 = reduce_chunk(v1, colbase + 32, g1, raw_tag);
-            const float c2 = reduce_chunk(v2, colbase + 64, g2, raw_tag), c3 = reduce_chunk(v3, colbase + 96, g3, raw_tag);
+            c0 = reduce_chunk(v0, colbase, g0, raw_tag); c1 = reduce_chunk(v1, colbase + 32, g1, raw_tag);
+            c2 = reduce_chunk(v2, colbase + 64, g2, raw_tag); c3 = reduce_chunk(v3, colbase + 96, g3, raw_tag);
+        };
+        auto append_batch = [&](int colbase) {
             m_run = fmaxf(max3(m_run, c0, c1), fmaxf(c2, c3));
-#if TC_EXP == 8
+#if TC_EXP == 7 || TC_EXP == 8
             return;
 #endif
             const float thr = m_run - band;
@@ -388,23 +390,26 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 #endif
             tc_fence_after();
             __syncwarp();
-#pragma unroll
-            for (int b2 = 0; b2 < 2; ++b2) {                          // two batches of 128 columns
-                const int cbb = cb + b2 * 128;
-                const bool raw = uniform && t_begin * TC_BN + cbb + 128 <= N;    // no padding columns to mask and uniform norms
-                tmem_ld32_issue(t0 + b2 * 128, va); tmem_ld32_issue(t0 + b2 * 128 + 32, vb);
-                tmem_ld32_issue(t0 + b2 * 128 + 64, vc); tmem_ld32_issue(t0 + b2 * 128 + 96, vd);
-                TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb); tmem_ld_pin(vc); tmem_ld_pin(vd));
-                if (b2 == 1) {
-                    tc_fence_before();                                // all TMEM reads of this tile are complete
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.acc_empty[half]);
-                }
-                TCT(tq_proc,
-                if (raw) process_batch(va, vb, vc, vd, cbb, std::true_type{});
-                else process_batch(va, vb, vc, vd, cbb, std::false_type{});)
-                TCT(tq_cmp, if (p8 > p8_high) compact());
-            }
+            // two batches of 128 columns; the second load is in flight while the first batch's events are appended
+            const bool raw0 = uniform && t_begin * TC_BN + cb + 128 <= N;        // no padding columns to mask and uniform norms
+            const bool raw1 = uniform && t_begin * TC_BN + cb + 256 <= N;
+            tmem_ld32_issue(t0, va); tmem_ld32_issue(t0 + 32, vb); tmem_ld32_issue(t0 + 64, vc); tmem_ld32_issue(t0 + 96, vd);
+            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb); tmem_ld_pin(vc); tmem_ld_pin(vd));
+            TCT(tq_proc,
+            if (raw0) reduce_batch(va, vb, vc, vd, cb, std::true_type{});
+            else reduce_batch(va, vb, vc, vd, cb, std::false_type{});)
+            tmem_ld32_issue(t0 + 128, va); tmem_ld32_issue(t0 + 160, vb); tmem_ld32_issue(t0 + 192, vc); tmem_ld32_issue(t0 + 224, vd);
+            TCT(tq_proc, append_batch(cb));
+            TCT(tq_cmp, if (p8 > p8_high) compact());
+            TCT(tq_ld, tmem_ld_wait(va); tmem_ld_pin(vb); tmem_ld_pin(vc); tmem_ld_pin(vd));
+            tc_fence_before();                                        // all TMEM reads of this tile are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[half]);
+            TCT(tq_proc,
+            if (raw1) reduce_batch(va, vb, vc, vd, cb + 128, std::true_type{});
+            else reduce_batch(va, vb, vc, vd, cb + 128, std::false_type{});
+            append_batch(cb + 128);)
+            TCT(tq_cmp, if (p8 > p8_high) compact());
         }
 
 #ifdef TC_TIMING

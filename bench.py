@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config id (1-5); 2 is the one the metric is quoted on")
     ap.add_argument("--pairs", type=int, default=0, help="override the number of pairs per GPU (0 = the config's)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU baseline sample (0 = 4 per host thread)")
-    ap.add_argument("--k1-algo", type=int, default=1, help="0 = FP32 FFMA2 mutual-NN kernel, 1 = tcgen05 TF32 filter + exact FP32 re-check (bit-identical results)")
+    ap.add_argument("--k1-algo", type=int, default=1, help="0 = FP32 FFMA2 mutual-NN kernel, 1 = tcgen05 bf16 filter + exact FP32 re-check (bit-identical results)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -288,7 +288,20 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         same = bool(torch.equal(Th, T.cpu()))
-        e2e = {"value": world * P * args.steps / tt.item(), "unit": UNIT,
+        # context for the e2e number: the bare host->device copy of one step's inputs (pinned, one stream), outside the timed region
+        dbuf = [torch.empty_like(x, device=dev) for x in h]
+        ca, cb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h2d_ms = []
+        for _ in range(3):
+            ca.record()
+            for d_, x in zip(dbuf, h):
+                d_.copy_(x, non_blocking=True)
+            cb_.record(); cb_.synchronize()
+            h2d_ms.append(ca.elapsed_time(cb_))
+        del dbuf
+        h2d_ms = min(h2d_ms)
+        e2e = {"value": world * P * args.steps / tt.item(), "unit": UNIT, "ms_per_step": tt.item() / args.steps * 1e3,
+               "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gbs": sum(x.numel() * 4 for x in h) / (h2d_ms * 1e-3) * 1e-9,
                "h2d_bytes_per_step": int(sum(x.numel() * 4 for x in h)), "d2h_bytes_per_step": int(Th.numel() * 4 + nmh.numel() * 4 + nih.numel() * 4),
                "api": "buffer_b200.backend.HostRegistrar.run -> bfr_register_uniform_host (pinned host buffers, %d-pair chunks on 2 streams)" % chunk,
                "poses_equal_device_path": same, "launches_per_step": (9 if args.k1_algo == 1 else 8) * ((P + chunk - 1) // chunk)}
@@ -310,14 +323,20 @@ def main():
                                     "(theoretical 148 SM x 128 lanes x 2 x 1.965 GHz = 74.4 TFLOP/s)",
                      "outputs_identical_to_tensor_path": k1_paths_identical}
         if args.k1_algo == 1:
-            tf32_peak = (mp.get("bf16_tflops") or 1590.0) / 2.0
-            roof = {"kernel": "k1_tc_kernel x2 (tcgen05 TF32 filter + exact FP32 re-check; src->tgt and tgt->src)", "bound": "tensor",
-                    "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
+            bf16_peak = mp.get("bf16_tflops") or 1590.0
+            # tensor-pipe floor of this formulation: one accumulator tile = 128 own rows x 256 streamed rows x K 32 = two back-to-back bf16 MMAs;
+            # the pipe drains on every switch to another accumulator tile, ~345 cycles per tile whatever its N (profiles/r01_mma_pipeline_microbench.txt)
+            tiles = 2.0 * P * ((N + 127) // 128) * ((N + 255) // 256)
+            mma_floor_ms = tiles / 148.0 * 345.0 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)
+            roof = {"kernel": "k1_tc_kernel x2 (tcgen05 bf16 filter, 128x256 accumulator tiles in TMEM + exact FP32 re-check; src->tgt and tgt->src)", "bound": "tensor",
+                    "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": traffic,
                     "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step, "algorithmic_flops_per_launch": flops_k1,
                     "executed_tensor_flops_per_launch": 2 * flops_k1,
-                    "peak_source": "TF32 dense = half of the measured cuBLAS bf16 burst peak in MEASURED_PEAKS.json (%s)" % ("measured" if mp.get("bf16_tflops") else "fallback 1.59 PF"),
-                    "note": "K = 32 makes this kernel epilogue-bound (TMEM -> register max-reduction), not MMA-bound; the algorithmic FLOP rate exceeds "
-                            "the FP32 roofline because the products run on tensor cores and only near-best candidates are re-evaluated in FP32",
+                    "peak_source": "dense bf16 = measured cuBLAS burst peak in MEASURED_PEAKS.json (%s)" % ("measured" if mp.get("bf16_tflops") else "fallback 1.59 PF"),
+                    "tensor_pipe_floor_ms": mma_floor_ms, "frac_of_tensor_pipe_floor": mma_floor_ms / k1_ms,
+                    "note": "K = 32 gives two MMAs per accumulator tile, so the tensor pipe is bound by its ~345-cycle drain per tile (tensor_pipe_floor_ms), "
+                            "not by FLOPs, and the kernel as a whole by the TMEM -> register max-reduction epilogue and the MMA <-> epilogue hand-off; "
+                            "the algorithmic FLOP rate exceeds the FP32 roofline because the products run on tensor cores and only near-best candidates are re-evaluated in FP32",
                     "vs_fp32_ffma2_peak": ach / peak_tf, "hbm_peak_gbs_measured": mp.get("hbm_gbs")}
         else:
             roof = dict(fp32_roof, traffic=traffic, k1_ms_per_launch=k1_ms, k1_share_of_step=k1_ms / ms_step, algorithmic_flops_per_launch=flops_k1)

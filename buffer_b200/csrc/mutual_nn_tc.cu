@@ -412,6 +412,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             TCT(tq_cmp, if (p8 > p8_high) compact());
         }
 
+        // The group list below reuses the TMA ring: every MMA of BOTH row halves must have read its stage first.  A warp knows that only
+        // for its own half (its last acc_full wait), so the epilogue warps meet once here (named barrier 1; warps 0 and 1 are not part).
+        asm volatile("bar.sync 1, %0;" ::"r"(128 * halves) : "memory");
 #ifdef TC_TIMING
         tq2 = clock64();
 #endif

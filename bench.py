@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--pairs", type=int, default=0, help="override the number of pairs per GPU (0 = the config's)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU baseline sample (0 = 4 per host thread)")
     ap.add_argument("--k1-algo", type=int, default=1, help="0 = FP32 FFMA2 mutual-NN kernel, 1 = tcgen05 bf16 filter + exact FP32 re-check (bit-identical results)")
+    ap.add_argument("--e2e-chunk", type=int, default=64, help="pairs per host->device chunk of the e2e leg (two chunks in flight on two streams)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -274,7 +275,7 @@ def main():
         pin = lambda x: x.contiguous().pin_memory()
         h = [pin(hb.src_des), pin(hb.src_xyz), pin(hb.tgt_des), pin(hb.tgt_xyz)]
         Th = torch.empty(P, 4, 4).pin_memory(); nmh = torch.empty(P, dtype=torch.int32).pin_memory(); nih = torch.empty(P, dtype=torch.int32).pin_memory()
-        chunk = min(P, 256)
+        chunk = min(P, args.e2e_chunk)
         reg = B.HostRegistrar(chunk, N, N, dev, ransac_splits=None, **kw)
         for _ in range(2):
             reg.run(*h, Th, nmh, nih)

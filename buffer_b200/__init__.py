@@ -10,7 +10,7 @@ __version__ = "0.1.0"
 
 
 def __getattr__(name):          # backend (needs the built .so) is imported lazily
-    if name in ("backend", "install", "dist"):
+    if name in ("backend", "install", "dist", "evaluation"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -132,5 +132,96 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+# ---- evaluation helpers (second half): ThreeDMatch/test.py:18-197 ---------------------------------------------
+def reference_eval_functions():
+    """The reference keeps its evaluator inside a script whose module level loads the model, the data loaders and nibabel.  Only the five
+    function definitions are needed, so they are compiled UNMODIFIED from the file's AST and run in a namespace that provides numpy and an
+    `nq` stub: nibabel (third-party, absent here) is replaced by the restatement of its `mat2quat` in buffer_b200/evaluation.py, which the
+    test additionally cross-checks against scipy's Rotation."""
+    import ast
+    import types
+    from buffer_b200 import evaluation as E
+    path = os.path.join(RI.REF_ROOT, "ThreeDMatch", "test.py")
+    tree = ast.parse(open(path).read())
+    mod = ast.Module(body=[n for n in tree.body if isinstance(n, ast.FunctionDef)], type_ignores=[])
+    ns = {"np": np, "nq": types.SimpleNamespace(mat2quat=E.mat2quat)}
+    exec(compile(mod, path, "exec"), ns)
+    return ns
+
+
+def gen_evaluation():
+    import tempfile
+    ns = reference_eval_functions()
+    rng = np.random.RandomState(31)
+    g = torch.Generator().manual_seed(77)
+    n_frag = 9
+    pairs = [(i, j) for i in range(n_frag) for j in range(i + 1, n_frag) if rng.rand() < 0.55]
+    gt = np.zeros((len(pairs), 4, 4)); gt[:, 3, 3] = 1
+    gt[:, :3, :3] = rot(g, len(pairs)); gt[:, :3, 3] = rng.randn(len(pairs), 3)
+    info = np.zeros((len(pairs), 6, 6))
+    for k in range(len(pairs)):
+        a = rng.randn(6, 6); info[k] = a @ a.T * 50 + np.eye(6) * 200
+    gt_log = "".join("%d\t %d\t %d\n" % (i, j, n_frag) + "".join("\t ".join(repr(float(v)) for v in row) + "\t \n" for row in gt[k])
+                     for k, (i, j) in enumerate(pairs))
+    gt_info = "".join("%d\t%d\t%d\n" % (i, j, n_frag) + "".join("\t".join(repr(float(v)) for v in row) + "\n" for row in info[k])
+                      for k, (i, j) in enumerate(pairs))
+    # estimates: most pairs of the ground truth (some perturbed slightly, some grossly) plus two pairs that are not in it
+    est_pairs, est = [], []
+    for k, (i, j) in enumerate(pairs):
+        if rng.rand() < 0.15:
+            continue
+        T = np.linalg.inv(gt[k])                      # the .log stores inv(T_est): a perfect estimate reproduces gt
+        kind = rng.rand()
+        if kind < 0.6:
+            d = np.eye(4); d[:3, :3] = S.quat_to_rot(torch.tensor([[1.0, 0.004, -0.003, 0.002]])).numpy()[0]; d[:3, 3] = rng.randn(3) * 0.01
+            T = T @ d
+        elif kind < 0.85:
+            d = np.eye(4); d[:3, :3] = rot(g, 1)[0]; d[:3, 3] = rng.randn(3) * 0.5
+            T = T @ d
+        est_pairs.append((i, j)); est.append(T)
+    for (i, j) in ((0, 1), (2, 3)):
+        if (i, j) not in pairs:
+            est_pairs.append((i, j)); est.append(np.eye(4))
+    with tempfile.TemporaryDirectory() as tmp:
+        open(os.path.join(tmp, "gt.log"), "w").write(gt_log)
+        open(os.path.join(tmp, "gt.info"), "w").write(gt_info)
+        gt_pairs_r, gt_traj_r = ns["read_trajectory"](os.path.join(tmp, "gt.log"))
+        n_fr, gt_info_r = ns["read_trajectory_info"](os.path.join(tmp, "gt.info"))
+        # the reference's own writer lines (ThreeDMatch/test.py:250-261), verbatim semantics
+        est_log = os.path.join(tmp, "est.log")
+        with open(est_log, "a+") as f:
+            for (i, j), T in zip(est_pairs, est):
+                trans = np.linalg.inv(T)
+                f.write(f'{i}\t {j}\t  1\n')
+                for r in range(4):
+                    f.write(f"{trans[r, 0]}\t {trans[r, 1]}\t {trans[r, 2]}\t {trans[r, 3]}\t \n")
+        est_log_text = open(est_log).read()
+        est_pairs_r, est_traj_r = ns["read_trajectory"](est_log)
+        precision, recall, flags, errors = ns["evaluate_registration"](n_fr, est_traj_r, est_pairs_r, gt_pairs_r, gt_traj_r, gt_info_r)
+        ext = ns["extract_corresponding_trajectors"](est_pairs_r[:5].copy(), gt_pairs_r, gt_traj_r) if all(tuple(int(x) for x in p[:2]) in pairs for p in est_pairs_r[:5]) else np.zeros((0, 4, 4))
+        terr = np.array([ns["computeTransformationErr"](np.linalg.inv(gt_traj_r[k]) @ est_traj_r[min(k, len(est_traj_r) - 1)], gt_info_r[k]) for k in range(min(6, len(pairs)))])
+    # the inline "recall of DGR" block (ThreeDMatch/test.py:263-283), restated verbatim on the same estimates
+    import math
+    states = []
+    gt_of_est = {p: gt[k] for k, p in enumerate(pairs)}
+    te_in, tg_in = [], []
+    for p, T in zip(est_pairs, est):
+        if p not in gt_of_est:
+            continue
+        trans_est, trans = T, np.linalg.inv(gt_of_est[p])
+        rte = np.linalg.norm(trans_est[:3, 3] - trans[:3, 3])
+        rre = np.arccos(np.clip((np.trace(trans_est[:3, :3].T @ trans[:3, :3]) - 1) / 2, -1 + 1e-16, 1 - 1e-16)) * 180 / math.pi
+        states.append(np.array([rte < 0.3 and rre < 15, rte, rre])); te_in.append(trans_est); tg_in.append(trans)
+    states = np.array(states)
+    np.savez(os.path.join(OUT, "evaluation.npz"), gt_log=gt_log, gt_info=gt_info, est_log=est_log_text, est_pairs=np.array(est_pairs), est=np.array(est),
+             gt_pairs_r=gt_pairs_r, gt_traj_r=gt_traj_r, n_fr=n_fr, gt_info_r=gt_info_r, est_pairs_r=est_pairs_r, est_traj_r=est_traj_r,
+             precision=precision, recall=recall, flags=np.array(flags), errors=errors, ext=ext, terr=terr,
+             dgr_states=states, dgr_est=np.array(te_in), dgr_gt=np.array(tg_in),
+             dgr_recall=states[:, 0].sum() / states.shape[0], dgr_te=states[states[:, 0] == 1, 1].mean(), dgr_re=states[states[:, 0] == 1, 2].mean())
+    print("evaluation.npz: %d gt pairs, %d estimates, precision %.3f recall %.3f, DGR recall %.3f" % (len(pairs), len(est_pairs), precision, recall, states[:, 0].mean()))
+
+
 if __name__ == "__main__":
-    main()
+    if "--evaluation" not in sys.argv:      # `--evaluation`: only (re)generate evaluation.npz
+        main()
+    gen_evaluation()

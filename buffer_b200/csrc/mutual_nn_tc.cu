@@ -1,23 +1,27 @@
 // mutual_nn_tc.cu — K1-TC: tensor-core *filter* + exact FP32 re-check for the mutual-NN argmax (sm_100a, tcgen05/TMEM/TMA).
 //
 // Same contract and bit-exact results as k1_mutual_nn_kernel (mutual_nn.cu / oracle orc_mutual_nn), ~10x less FP32 work:
-//   1. S~ = A B^T with tcgen05.mma kind::tf32 (M=128, N=128, K=8 per instruction, accumulators in TMEM).  TF32 keeps 11
-//      significand bits, so |S~_ij - a_i.b_j| <= 2^-9 |a_i||b_j|; with eps = 2^-8 |a_i| max_j|b_j| every column whose exact
-//      score could be the row maximum satisfies  S~_ij + hn(b_j) >= max_j(S~_ij + hn(b_j)) - 2 eps.
-//   2. The epilogue (one thread per row, TMEM -> registers with tcgen05.ld) keeps the running approximate maximum and a
-//      short list of 4-column groups whose maximum was inside the 2-eps band when they streamed past (compacted when full).
-//   3. Each thread re-evaluates its few candidates with the EXACT FP32 chain of the oracle (acc = hn(b); acc = fma(a_k, b_k,
-//      acc), k ascending) and publishes (key << 32 | ~index) with the same 64-bit RED.MAX as the FP32 kernel, so ties still
-//      go to the lowest index and the result is bit-identical by construction.  A list overflow (many near-duplicate
-//      descriptors) falls back to an exact scan of the row.
+//   1. S~ = A B^T with tcgen05.mma kind::f16 on bf16 copies of the descriptors (written by k1_prep_kernel; M = 128, N = 256,
+//      K = 16 per instruction, FP32 accumulators in TMEM).  bf16 keeps 8 significand bits, so |S~_ij - a_i.b_j| <=
+//      (2^-8 + 2^-16) |a_i||b_j|; with eps = 1.024 * 2^-7 |a_i| max_j|b_j| every column whose exact score could be the row maximum
+//      satisfies  S~_ij + hn(b_j) >= max_j(S~_ij + hn(b_j)) - 2 eps.
+//   2. The epilogue (one thread per row, TMEM -> registers with tcgen05.ld) keeps the running approximate maximum and a short list of
+//      "events": 32-column chunks whose maximum was inside the 2-eps band when they streamed past, with their eight 4-column group
+//      maxima (compacted when the list runs low).
+//   3. Each thread re-evaluates the groups that are still in band at the end with the EXACT FP32 chain of the oracle (acc = hn(b);
+//      acc = fma(a_k, b_k, acc), k ascending) and publishes (key << 32 | ~index) with the same 64-bit RED.MAX as the FP32 kernel, so
+//      ties still go to the lowest index and the result is bit-identical by construction.  If an in-band event ever had to be
+//      dropped (many near-duplicate descriptors) the row falls back to an exact scan.
 // The column direction (tgt -> src) is the same kernel with the roles of the two descriptor sets swapped.
 //
-// Warp roles (320 threads, 1 CTA/SM, 256 own rows, 512 TMEM columns = 2 buffers x 2 row halves x 128 columns):
-//   warp 0   TMA producer: the CTA's 256 "own" rows once, then 128-row tiles of the streamed side through a 4-stage ring
-//            (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier expect-tx)
-//   warp 1   TMEM allocator + MMA issuer: 2 halves x 4 tcgen05.mma (K = 4 x 8) per tile, tcgen05.commit -> ring slot free / accumulator full
-//   warps 2-9 epilogue (one thread per own row): tcgen05.ld 32 columns at a time, add hn(b_j) (shared-memory broadcast),
-//            FMNMX3 tree per 4-column group, predicated append of the groups inside the band
+// Warp roles (320 threads, 1 CTA/SM, 256 own rows = 2 row halves, 512 TMEM columns = one 128 x 256 accumulator tile per half):
+//   warp 0   TMA producer: the CTA's 256 "own" rows once, then 256-row tiles of the streamed side through a 3-stage ring
+//            (cp.async.bulk.tensor.2d, SWIZZLE_64B, mbarrier expect-tx)
+//   warp 1   TMEM allocator + MMA issuer: per tile and half 2 x tcgen05.mma (K = 2 x 16), tcgen05.commit -> accumulator full / stage free
+//   warps 2-9 epilogue (one thread per own row): two batches of 4 x tcgen05.ld.32x32b.x32, (add hn(b_j),) FMNMX3 tree per 4-column
+//            group, predicated append of the chunks inside the band; the tile goes back to the MMA warp as soon as the second
+//            batch is in registers.  Why the tile is 128 x 256 and single-buffered per half: see the note in the epilogue.
+// -DTC_TIMING adds clock64 phase timers and event counters (tools/k1_bench.py prints them); it is never defined in the product build.
 #include "bfr_common.cuh"
 #include "bfr_kernels.h"
 #include <cuda.h>
@@ -30,26 +34,12 @@ namespace bfr {
 constexpr int TC_BM = 256;                      // own rows per CTA = two M=128 accumulator halves sharing every streamed tile
 constexpr int TC_BN = 256;                      // streamed rows per tile = MMA N (the largest cta_group::1 shape: see the note on accumulator switches below)
 constexpr int TC_D = 32;
-#ifndef TC_MMAK
-#define TC_MMAK (TC_D / 16)
-#endif
-#ifndef TC_STAGES_N
-#define TC_STAGES_N 3
-#endif
-#ifndef TC_CAP_N
-#define TC_CAP_N 13
-#endif
-constexpr int TC_STAGES = TC_STAGES_N;
+constexpr int TC_MMAK = TC_D / 16;                // K = 16 per bf16 MMA
+constexpr int TC_STAGES = 3;                     // streamed tiles in flight (3 x 16 KB)
 constexpr int TC_EPI_WARPS = 8;                 // one epilogue thread per own row
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-#ifndef TC_EXP
-#define TC_EXP 0
-#endif
-#ifndef TC_POLL
-#define TC_POLL 0
-#endif
 constexpr int TC_SUB = 4;                       // candidate granularity: 4-column groups
-constexpr int TC_CAP = TC_CAP_N;                      // band events (32-column chunks with their 8 group maxima) kept per row
+constexpr int TC_CAP = 13;                       // band events (32-column chunks with their 8 group maxima) kept per row
 constexpr int TC_GCAP = 32;                     // surviving 4-column groups per row handed to the exact re-check
 constexpr int TC_MAX_TILES = 24;                // streamed tiles per CTA (hn cache = 6144 floats)
 
@@ -79,17 +69,6 @@ constexpr uint32_t TC_CID_SLOT = sizeof(uint2) * 32;            // 256
 // p16 / p8 are the shared-memory addresses of this row's next free slot in cmg / cid.
 BFR_DEVINL void append_if_in_band(float c, float thr, uint32_t& p16, uint32_t& p8, const float (&mg)[8], uint32_t id)
 {
-#ifdef TC_BRANCH_APPEND
-    if (c >= thr) {
-        asm volatile("st.shared.v4.f32 [%0], {%2, %3, %4, %5};\n\t"
-                     "st.shared.v4.f32 [%0+512], {%6, %7, %8, %9};\n\t"
-                     "st.shared.v2.b32 [%1], {%10, %11};"
-                     :: "r"(p16), "r"(p8), "f"(mg[0]), "f"(mg[1]), "f"(mg[2]), "f"(mg[3]), "f"(mg[4]), "f"(mg[5]), "f"(mg[6]), "f"(mg[7]),
-                        "r"(__float_as_uint(c)), "r"(id) : "memory");
-        p16 += 1024; p8 += 256;
-    }
-    return;
-#endif
     asm volatile("{\n\t.reg .pred q;\n\t"
                  "setp.ge.f32 q, %2, %3;\n\t"
                  "@q st.shared.v4.f32 [%0], {%4, %5, %6, %7};\n\t"
@@ -104,14 +83,6 @@ BFR_DEVINL void append_if_in_band(float c, float thr, uint32_t& p16, uint32_t& p
 }
 static_assert(TC_CMG_HALF == 512 && TC_CMG_SLOT == 1024 && TC_CID_SLOT == 256, "append_if_in_band hard-codes these strides");
 
-BFR_DEVINL void mbar_spin(uint64_t* bar, uint32_t parity)
-{   // busy poll (test_wait never suspends the thread)
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "SPIN_%=:\n\t"
-        "mbarrier.test_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@!p bra SPIN_%=;\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 BFR_DEVINL void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -251,9 +222,6 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(&sm.empty[s], ph ^ 1u);
-#ifdef TC_NOTMA
-                if (it >= TC_STAGES) { mbar_arrive(&sm.full[s]); continue; }
-#endif
                 mbar_expect_tx(&sm.full[s], TC_BN * TC_D * 2);
                 tma_load_2d(sm.b[s], &map_str, 0, os + (t_begin + it) * TC_BN, &sm.full[s]);
             }
@@ -270,9 +238,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                 mbar_wait(&sm.full[s], ph);
                 const uint64_t bdesc = umma_desc_sw64(sm.b[s]);
                 for (int h = 0; h < halves; ++h) {                    // one accumulator tile (128 rows x 256 streamed columns) per row half
-#ifndef TC_NOWAIT
                     mbar_wait(&sm.acc_empty[h], ((uint32_t)it & 1u) ^ 1u);
-#endif
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)(h * TC_BN);
                     const uint64_t ad = h ? adesc1 : adesc0;
@@ -326,17 +292,11 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         // (tighter) threshold; a chunk whose maximum is inside the band keeps its eight group maxima as one event (predicated stores)
         float g0[8], g1[8], g2[8], g3[8], c0, c1, c2, c3;
         auto reduce_batch = [&](float (&v0)[32], float (&v1)[32], float (&v2)[32], float (&v3)[32], int colbase, auto raw_tag) {
-#if TC_EXP == 7
-            c0 = (v0[0] + v1[31]) + (v2[0] + v3[31]); c1 = c2 = c3 = c0; return;
-#endif
             c0 = reduce_chunk(v0, colbase, g0, raw_tag); c1 = reduce_chunk(v1, colbase + 32, g1, raw_tag);
             c2 = reduce_chunk(v2, colbase + 64, g2, raw_tag); c3 = reduce_chunk(v3, colbase + 96, g3, raw_tag);
         };
         auto append_batch = [&](int colbase) {
             m_run = fmaxf(max3(m_run, c0, c1), fmaxf(c2, c3));
-#if TC_EXP == 7 || TC_EXP == 8
-            return;
-#endif
             const float thr = m_run - band;
             append_if_in_band(c0, thr, p16, p8, g0, (uint32_t)colbase);
             append_if_in_band(c1, thr, p16, p8, g1, (uint32_t)(colbase + 32));
@@ -382,9 +342,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 #ifdef TC_TIMING
             const long long tw0 = clock64();
 #endif
-#ifndef TC_NOWAIT
             mbar_wait(&sm.acc_full[half], (uint32_t)it & 1u);
-#endif
 #ifdef TC_TIMING
             tq_wait += clock64() - tw0;
 #endif
@@ -443,7 +401,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             // surviving events -> list of in-band 4-column groups (global streamed column of each), in the idle TMA ring
             uint32_t (*glist)[TC_BM] = reinterpret_cast<uint32_t (*)[TC_BM]>(&sm.b[0][0]);
             int n = 0;
-            if (valid && !overflow && TC_EXP != 10 && TC_EXP != 11 && TC_EXP != 12) {
+            if (valid && !overflow) {
                 const int cnt = (int)((p8 - p8_base) / TC_CID_SLOT);
                 uint32_t q_ev = 0;                                    // events whose chunk maximum is still inside the band
 #pragma unroll

@@ -21,13 +21,18 @@ namespace bfr {
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_CHUNK = 2048;                  // correspondences per shared-memory chunk
-constexpr int RS_QCAP = 2 * RS_THREADS;
+#ifndef RS_S1_N
+#define RS_S1_N 4
+#endif
+constexpr int RS_S1 = RS_S1_N;                     // stage-1 hypotheses per thread and round
+constexpr int RS_QCAP = 2 * RS_THREADS;            // queue 2 holds < RS_THREADS leftovers plus the survivors of one fit block
+constexpr int RS_Q1CAP = (1 + RS_S1) * RS_THREADS; // queue 1 holds < RS_THREADS leftovers plus one round's survivors
 
 struct __align__(16) RsSmem {
     float4 chunk[RS_CHUNK / 2][4];              // per pair of correspondences: (sx sx' sy sy')(sz sz' qx qx')(qy qy' qz qz')(w w' - -)
     float q[12][RS_QCAP];                       // queue 2: hypotheses that passed every check: R (9) + t (3), SoA
     uint32_t qh[RS_QCAP];
-    uint4 q1[RS_QCAP];                          // queue 1: survivors of the cheap checks: {h, i0, i1, i2}
+    uint4 q1[RS_Q1CAP];                        // queue 1: survivors of the cheap checks: {h, i0, i1, i2}
     int q1count;
     unsigned long long red[RS_THREADS / 32];
     int qcount;
@@ -139,11 +144,11 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
 
     // stage 2 on n queue-1 entries (thread i takes entry i): Kabsch + distance check on dense warps, survivors -> queue 2;
     // scores a full block of queue 2 whenever one is available
-    auto fit_queue1 = [&](int n) {
+    auto fit_queue1 = [&](int base, int n) {
         float R[9], t[3];
         bool ok = false; uint32_t h = 0;
         if ((int)threadIdx.x < n) {
-            const uint4 e = sm.q1[threadIdx.x];
+            const uint4 e = sm.q1[base + threadIdx.x];
             h = e.x;
             const uint32_t id[3] = { e.y, e.z, e.w };
             float s[3][3], q[3][3];
@@ -187,27 +192,36 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         }
     };
 
-    for (uint32_t base = hb; base < he; base += RS_THREADS) {
-        // stage 1: one hypothesis per thread, cheap checks only (~10 % survive at 70 % outliers)
-        const uint32_t h = base + threadIdx.x;
-        uint32_t id[3] = { 0u, 0u, 0u };
-        bool ok = false;
-        if (h < he) { float s[3][3], q[3][3]; ok = hypothesis_precheck(corr_p, (uint32_t)K, seed, pair_id, h, sim2, id, s, q); }
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (bal) {
-            int pos = 0;
-            if (lane == 0) pos = atomicAdd(&sm.q1count, __popc(bal));
-            pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-            if (ok) sm.q1[pos] = make_uint4(h, id[0], id[1], id[2]);
+    for (uint32_t base = hb; base < he; base += RS_S1 * RS_THREADS) {
+        // stage 1: RS_S1 independent hypotheses per thread (their sample gathers overlap), cheap checks only (~10 % survive at 70 % outliers)
+        uint32_t hh[RS_S1], id[RS_S1][3];
+        bool ok[RS_S1];
+#pragma unroll
+        for (int u = 0; u < RS_S1; ++u) {
+            hh[u] = base + (uint32_t)u * RS_THREADS + threadIdx.x;
+            id[u][0] = id[u][1] = id[u][2] = 0u;
+            ok[u] = false;
+            if (hh[u] < he) { float s[3][3], q[3][3]; ok[u] = hypothesis_precheck(corr_p, (uint32_t)K, seed, pair_id, hh[u], sim2, id[u], s, q); }
+        }
+#pragma unroll
+        for (int u = 0; u < RS_S1; ++u) {                              // queue order = hypothesis order within the round (any order gives the same best)
+            const unsigned bal = __ballot_sync(0xffffffffu, ok[u]);
+            if (bal) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(&sm.q1count, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (ok[u]) sm.q1[pos] = make_uint4(hh[u], id[u][0], id[u][1], id[u][2]);
+            }
         }
         __syncthreads();
         const int n1 = sm.q1count;
         __syncthreads();                       // everyone has read q1count before it changes
         if (n1 >= RS_THREADS) {
-            fit_queue1(RS_THREADS);
-            const int rem = n1 - RS_THREADS;
+            int done = 0;
+            for (; n1 - done >= RS_THREADS; done += RS_THREADS) fit_queue1(done, RS_THREADS);
+            const int rem = n1 - done;                                 // < RS_THREADS leftovers move to the front
             uint4 mv = make_uint4(0u, 0u, 0u, 0u);
-            if ((int)threadIdx.x < rem) mv = sm.q1[RS_THREADS + threadIdx.x];
+            if ((int)threadIdx.x < rem) mv = sm.q1[done + threadIdx.x];
             __syncthreads();
             if ((int)threadIdx.x < rem) sm.q1[threadIdx.x] = mv;
             if (threadIdx.x == 0) sm.q1count = rem;
@@ -217,7 +231,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
     {
         const int n1 = sm.q1count;             // flush queue 1, then queue 2
         __syncthreads();
-        if (n1 > 0) fit_queue1(n1);
+        if (n1 > 0) fit_queue1(0, n1);
     }
     const int qn = sm.qcount;
     if (qn > 0) { score_queue(sm, corr_p, K, qn, d2max, best); n_scored += qn; }

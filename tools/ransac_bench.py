@@ -1,0 +1,29 @@
+#!/usr/bin/env python3
+"""RANSAC-only timing on the bench workload: python tools/ransac_bench.py [pairs] [splits ...]  -> ms per launch for each split count"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from buffer_b200 import _lib
+if os.environ.get("BFR_SO"): _lib.SO_PATH = os.path.abspath(os.environ["BFR_SO"])      # experiment variants (tools/build_variant.sh)
+from buffer_b200 import backend as B, synthetic as S
+P = int(sys.argv[1]) if len(sys.argv) > 1 else 1623
+splits = [int(x) for x in sys.argv[2:]] or [1, 2, 3, 4]
+c = S.CONFIGS[2]; N = c["gen"]["num_kpts"]; dev = "cuda:0"
+parts = [S.make_pairs(min(128, P - p0), first_pair=p0, device=dev, **c["gen"]) for p0 in range(0, P, 128)]
+cat = lambda f: torch.cat([getattr(b, f) for b in parts], 0)
+src_des, tgt_des = cat("src_des").reshape(P * N, 32), cat("tgt_des").reshape(P * N, 32)
+src_xyz, tgt_xyz = cat("src_xyz").reshape(P * N, 3), cat("tgt_xyz").reshape(P * N, 3)
+off = (torch.arange(P + 1, dtype=torch.int32) * N).to(dev)
+rm = B.mutual_matching_batched(src_des, tgt_des, off, off, N, N, src_xyz, tgt_xyz, want_nn=False, want_mids=False)
+ref = None
+for s in splits:
+    best = None; ms = []
+    for i in range(4):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        out = B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], seed=0, pair_id_base=0, splits=s)
+        eb.record(); eb.synchronize(); ms.append(ea.elapsed_time(eb))
+    T = out[0] if isinstance(out, (tuple, list)) else out
+    same = True if ref is None else bool(torch.equal(T, ref))
+    if ref is None: ref = T.clone()
+    print("splits %d: %.3f ms (min of 3 warm runs), identical to splits[0]: %s" % (s, min(ms[1:]), same))

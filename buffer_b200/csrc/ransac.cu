@@ -59,9 +59,9 @@ BFR_DEVINL void count_if_lt(int& count, float d, float thr)
     asm("{\n\t.reg .pred q;\n\tsetp.lt.f32 q, %1, %2;\n\t@q add.s32 %0, %0, 1;\n\t}" : "+r"(count) : "f"(d), "f"(thr));
 }
 
-// inlier count of one hypothesis over the chunk currently in shared memory (npairs pairs of correspondences)
+// inlier count of one hypothesis over pairs [g_begin, g_end) of the chunk currently in shared memory
 template <bool PER_CORR_THR>
-BFR_DEVINL int score_chunk(const RsSmem& sm, int npairs, const float R[9], const float t[3], float d2max)
+BFR_DEVINL int score_chunk(const RsSmem& sm, int g_begin, int g_end, const float R[9], const float t[3], float d2max)
 {
     f32x2 Rb[9], tb[3];
 #pragma unroll
@@ -70,7 +70,7 @@ BFR_DEVINL int score_chunk(const RsSmem& sm, int npairs, const float R[9], const
     for (int k = 0; k < 3; ++k) tb[k] = pack2(t[k], t[k]);
     int count = 0;
 #pragma unroll 4
-    for (int g = 0; g < npairs; ++g) {
+    for (int g = g_begin; g < g_end; ++g) {
         const float4 L0 = sm.chunk[g][0], L1 = sm.chunk[g][1], L2 = sm.chunk[g][2];     // warp-uniform -> broadcast
         const f32x2 sx = pack2(L0.x, L0.y), sy = pack2(L0.z, L0.w), sz = pack2(L1.x, L1.y);
         const f32x2 qx = pack2(L1.z, L1.w), qy = pack2(L2.x, L2.y), qz = pack2(L2.z, L2.w);
@@ -92,28 +92,42 @@ BFR_DEVINL int score_chunk(const RsSmem& sm, int npairs, const float R[9], const
     return count;
 }
 
-// score `n` queued hypotheses (thread i takes queue entry i) against all K correspondences; fold into `best`
+// score `n` queued hypotheses against all K correspondences; fold into `best`.  A full queue (n = RS_THREADS) gives every thread one
+// hypothesis.  A partial flush (n < RS_THREADS) would leave most warps idle while the chunks still stream through shared memory, so the
+// nw = ceil(n / 32) warps' worth of hypotheses are replicated over the 8 / nw groups of warps and every group scores its own slice of each
+// chunk (the loads stay warp-uniform broadcasts); the partial counts are integer sums, so the total is exact whatever the split.
 BFR_DEVINL void score_queue(RsSmem& sm, const float4* __restrict__ corr, int K, int n, float d2max, unsigned long long& best)
 {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nw = (n + 31) >> 5;                                     // warps that hold hypotheses
+    const int nparts = (RS_THREADS / 32) / nw;                        // correspondence slices (1 for a full queue)
+    const int part = warp / nw, hi = (warp % nw) * 32 + lane;         // this thread: hypothesis hi of the queue, slice `part`
+    const bool warp_has_work = part < nparts;
+    const bool mine = warp_has_work && hi < n;
     float R[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f }, t[3] = { 0.f, 0.f, 0.f }; uint32_t h = 0;
-    const bool mine = (int)threadIdx.x < n;
     if (mine) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = sm.q[k][threadIdx.x];
+        for (int k = 0; k < 9; ++k) R[k] = sm.q[k][hi];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) t[k] = sm.q[9 + k][threadIdx.x];
-        h = sm.qh[threadIdx.x];
+        for (int k = 0; k < 3; ++k) t[k] = sm.q[9 + k][hi];
+        h = sm.qh[hi];
     }
-    const bool warp_has_work = (int)(threadIdx.x & ~31u) < n;
+    int* partial = reinterpret_cast<int*>(sm.q1);                     // queue 1 is empty whenever a partial flush runs
+    if (nparts > 1) partial[threadIdx.x] = 0;                         // (made visible by the barriers of the chunk loop)
     int count = 0;
     for (int c0 = 0; c0 < K; c0 += RS_CHUNK) {
         __syncthreads();                       // previous chunk fully consumed
         load_chunk(sm, corr, K, c0);
         __syncthreads();
         const int npairs = (min(RS_CHUNK, K - c0) + 1) >> 1;
-        if (warp_has_work) count += score_chunk<false>(sm, npairs, R, t, d2max);
+        if (warp_has_work) count += score_chunk<false>(sm, (part * npairs) / nparts, ((part + 1) * npairs) / nparts, R, t, d2max);
     }
-    if (mine) {
+    if (nparts > 1) {
+        if (mine) atomicAdd(&partial[hi], count);
+        __syncthreads();
+        count = partial[hi < RS_THREADS ? hi : 0];
+    }
+    if (mine && part == 0) {
         const unsigned long long packed = ((unsigned long long)(uint32_t)count << 32) | (unsigned long long)(0xFFFFFFFFu - h);
         best = packed > best ? packed : best;
     }
@@ -341,7 +355,7 @@ score_hypotheses_kernel(const float* __restrict__ Rh, const float* __restrict__ 
         load_chunk(sm, rec, C, c0);
         __syncthreads();
         const int npairs = (min(RS_CHUNK, C - c0) + 1) >> 1;
-        if (warp_has_work) count += score_chunk<true>(sm, npairs, R, t, 0.0f);
+        if (warp_has_work) count += score_chunk<true>(sm, 0, npairs, R, t, 0.0f);
     }
     unsigned long long best = 0ull;
     if (mine) {

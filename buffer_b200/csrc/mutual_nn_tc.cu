@@ -60,7 +60,8 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 static_assert(sizeof(uint16_t) * TC_STAGES * TC_BN * TC_D >= sizeof(uint32_t) * TC_GCAP * TC_BM, "group list must fit in the TMA ring");
-static_assert(sizeof(TcSmem::Ev) >= 4 * 256 * sizeof(float4), "a warp's event slice doubles as its 16 KB staging area (4 candidate columns x 32 rows x 128 B)");
+static_assert(sizeof(TcSmem::Ev) >= 4 * 256 * sizeof(float4) + 32 * sizeof(unsigned long long), "a warp's event slice doubles as its 16 KB staging area (4 candidate columns x 32 rows x 128 B) + 32 packed row maxima");
+static_assert(TC_STAGES >= 3 && TC_GCAP * TC_BM * sizeof(uint32_t) <= 2 * TC_BN * TC_D * sizeof(uint16_t), "the group list must leave the third TMA stage free for the staged own rows");
 constexpr uint32_t TC_CMG_HALF = sizeof(float4) * 32;           // 512: second half of an event's group maxima
 constexpr uint32_t TC_CMG_SLOT = 2 * TC_CMG_HALF;               // 1024
 constexpr uint32_t TC_CID_SLOT = sizeof(uint2) * 32;            // 256
@@ -434,18 +435,38 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 #pragma unroll
                 for (int c = 0; c < 8; ++c) rowv[c] = stage[buf * 256 + lane * 8 + (c ^ (lane & 7))];
             };
+            // own rows: staged once per warp in operand memory that is dead by now (the bf16 own tile / the third TMA stage), so that any
+            // lane can read any row of the warp in the balanced part below
+            float4* ownS = (ew < 4) ? reinterpret_cast<float4*>(sm.a) + ew * 256 : reinterpret_cast<float4*>(sm.b[2]) + (ew - 4) * 256;
+            unsigned long long* bestS = reinterpret_cast<unsigned long long*>(stage + TC_SUB * 256);      // per-row maxima of the balanced part
             float4 own[8];
-            put(0, reg[0]);
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) { const int rid = 4 * s8 + sub; ownS[rid * 8 + (chunk ^ (rid & 7))] = reg[0][s8]; }
+            bestS[lane] = 0ull;
             __syncwarp();
-            get(0, own);
-            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) own[c] = ownS[lane * 8 + (c ^ (lane & 7))];
             const int nmax = __reduce_max_sync(0xffffffffu, n);
 #ifdef TC_TIMING
             tv_own = clock64(); tv_rounds = nmax;
 #endif
             const float* xs = x_str + (size_t)os * TC_D;
-            for (int k = 0; k < nmax; ++k) {
-                const int j0 = (k < n) ? (int)glist[k][r] : -0x40000000;     // first column of this lane's k-th group
+            // exact score of (own row values o, its half-norm ohn) against streamed column j whose row is in staging buffer `buf`
+            auto exact_staged = [&](const float4 (&o)[8], float ohn, int buf, int j) -> float {
+                float4 c[8];
+                get(buf, c);
+                const float cand_hn = sm.hn[j - t_begin * TC_BN];
+                float acc = COLDIR ? ohn : cand_hn;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    acc = __fmaf_rn(o[k4].x, c[k4].x, acc); acc = __fmaf_rn(o[k4].y, c[k4].y, acc);
+                    acc = __fmaf_rn(o[k4].z, c[k4].z, acc); acc = __fmaf_rn(o[k4].w, c[k4].w, acc);
+                }
+                return COLDIR ? __fadd_rn(acc, cand_hn) : acc;
+            };
+            // first group of every row: lane = row, the four columns of the group in one memory round trip
+            if (nmax > 0) {
+                const int j0 = (n > 0) ? (int)glist[0][r] : -0x40000000;
                 int jc[TC_SUB];
 #pragma unroll
                 for (int u = 0; u < TC_SUB; ++u) { jc[u] = (j0 >= 0 && j0 + u < j_end) ? j0 + u : -1; fetch(xs, jc[u], reg[u]); }
@@ -461,29 +482,79 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 #pragma unroll
                 for (int u = 0; u < TC_SUB; ++u) {
                     if (jc[u] >= 0) {
-                        float4 c[8];
-                        get(u, c);
-                        const float cand_hn = sm.hn[jc[u] - t_begin * TC_BN];
-                        float acc = COLDIR ? own_hn : cand_hn;
-#pragma unroll
-                        for (int k4 = 0; k4 < 8; ++k4) {
-                            acc = __fmaf_rn(own[k4].x, c[k4].x, acc); acc = __fmaf_rn(own[k4].y, c[k4].y, acc);
-                            acc = __fmaf_rn(own[k4].z, c[k4].z, acc); acc = __fmaf_rn(own[k4].w, c[k4].w, acc);
-                        }
-                        const float e = COLDIR ? __fadd_rn(acc, cand_hn) : acc;
+                        const float e = exact_staged(own, own_hn, u, jc[u]);
                         if (e > best || (e == best && jc[u] < best_j)) { best = e; best_j = jc[u]; }
                     }
                 }
                 __syncwarp();
             }
-            if (valid && overflow) {                                  // pathological row (many near-duplicates): exact scan
-                for (int j = t_begin * TC_BN; j < j_end; ++j) {
-                    const float e = exact_score<COLDIR>(own, own_hn, xs + (size_t)j * TC_D, hn_str_p[j]);
-                    if (e > best) { best = e; best_j = j; }
+            // further groups (rows without a clear winner have a few): a warp would need as many rounds as its busiest lane, so the
+            // remaining (row, group) items are flattened level by level (level k = the rows that have a k-th group) and dealt out evenly,
+            // one (group, column) per lane and staging buffer; per-row maxima meet in shared memory (atom.max on the packed key)
+            if (nmax > 1) {
+                int total = 0;
+                for (int kk = 1; kk < nmax; ++kk) total += __popc(__ballot_sync(0xffffffffu, n > kk));
+                const int rbase = r - lane;                           // tile row of lane 0
+                for (int base = 0; base < TC_SUB * total; base += TC_SUB * 32) {
+                    int jc[TC_SUB], rl[TC_SUB];
+#pragma unroll
+                    for (int u = 0; u < TC_SUB; ++u) {
+                        const int item = base + u * 32 + lane;
+                        int rem = item >> 2, src = -1, kf = 0;       // item -> (level kf, rem-th row of that level)
+                        for (int kk = 1; kk < nmax; ++kk) {
+                            unsigned m = __ballot_sync(0xffffffffu, n > kk);
+                            const int cnt = __popc(m);
+                            if (src < 0) {
+                                if (rem < cnt) { for (int q2 = 0; q2 < rem; ++q2) m &= m - 1u; src = __ffs((int)m) - 1; kf = kk; }
+                                else rem -= cnt;
+                            }
+                        }
+                        const int j0 = (src >= 0) ? (int)glist[kf][rbase + src] : -0x40000000;
+                        jc[u] = (j0 >= 0 && j0 + (item & 3) < j_end) ? j0 + (item & 3) : -1;
+                        rl[u] = src >= 0 ? src : 0;
+                        fetch(xs, jc[u], reg[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < TC_SUB; ++u) put(u, reg[u]);
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < TC_SUB; ++u) {
+                        const float ohn = __shfl_sync(0xffffffffu, own_hn, rl[u]);
+                        if (jc[u] >= 0) {
+                            float4 o[8];
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) o[c] = ownS[rl[u] * 8 + (c ^ (rl[u] & 7))];
+                            const float e = exact_staged(o, ohn, u, jc[u]);
+                            atomicMax(&bestS[rl[u]], pack_best(float_key(e), (uint32_t)jc[u]));
+                        }
+                    }
+                    __syncwarp();
                 }
             }
-            if (valid && best_j != 0x7fffffff)
-                red_max_u64(out_packed + (size_t)p * pad_own + row, pack_best(float_key(best), (uint32_t)best_j));
+            // pathological rows (an in-band event had to be dropped: many near-duplicates, or ten chunks within the band of the maximum): exact
+            // scan of the row, done by the whole warp (lane l takes columns l, l + 32, ...) - a single lane would hold its SM for milliseconds
+            unsigned long long scan_best = 0ull;
+            for (unsigned ovm = __ballot_sync(0xffffffffu, valid && overflow); ovm; ovm &= ovm - 1u) {
+                const int src = __ffs((int)ovm) - 1;
+                float4 o[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) o[c] = ownS[src * 8 + (c ^ (src & 7))];
+                const float ohn = __shfl_sync(0xffffffffu, own_hn, src);
+                float sb = -INFINITY; int sj = 0x7fffffff;
+#pragma unroll 2
+                for (int j = t_begin * TC_BN + lane; j < j_end; j += 32) {
+                    const float e = exact_score<COLDIR>(o, ohn, xs + (size_t)j * TC_D, hn_str_p[j]);
+                    if (e > sb) { sb = e; sj = j; }                   // ascending j per lane: strict > keeps the lowest index
+                }
+                unsigned long long pk = (sj != 0x7fffffff) ? pack_best(float_key(sb), (uint32_t)sj) : 0ull;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, pk, off); pk = other > pk ? other : pk; }
+                if (lane == src) scan_best = pk;
+            }
+            unsigned long long fin = (best_j != 0x7fffffff) ? pack_best(float_key(best), (uint32_t)best_j) : 0ull;
+            if (nmax > 1) { const unsigned long long other = bestS[lane]; fin = other > fin ? other : fin; }
+            fin = scan_best > fin ? scan_best : fin;
+            if (valid && fin != 0ull) red_max_u64(out_packed + (size_t)p * pad_own + row, fin);
         }
     }
 

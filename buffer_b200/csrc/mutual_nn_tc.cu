@@ -150,6 +150,90 @@ BFR_DEVINL float exact_score(const float4 (&own)[8], float own_hn, const float* 
     return COLDIR ? __fadd_rn(acc, cand_hn) : acc;
 }
 
+// exact scan of one row by a whole warp (lane l takes streamed columns j_begin + l, + 32, ...): the fallback for rows whose candidate list
+// overflowed.  `o` = the own row (every lane holds the same values), returns the packed best (key << 32 | ~index) in every lane.  Kept out of
+// line: it runs for a handful of rows per launch and must not cost the main path registers or instruction-cache lines.
+template <bool COLDIR>
+__device__ __noinline__ unsigned long long warp_exact_scan(const float4* __restrict__ own_row_smem, int swz, float ohn, const float* __restrict__ xs,
+                                                           const float* __restrict__ hn_str_p, int j_begin, int j_end)
+{
+    const int lane = threadIdx.x & 31;
+    float4 o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) o[c] = own_row_smem[c ^ swz];
+    float sb = -INFINITY; int sj = 0x7fffffff;
+#pragma unroll 2
+    for (int j = j_begin + lane; j < j_end; j += 32) {
+        const float e = exact_score<COLDIR>(o, ohn, xs + (size_t)j * TC_D, hn_str_p[j]);
+        if (e > sb) { sb = e; sj = j; }                               // ascending j per lane: strict > keeps the lowest index
+    }
+    unsigned long long pk = (sj != 0x7fffffff) ? pack_best(float_key(sb), (uint32_t)sj) : 0ull;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, pk, off); pk = other > pk ? other : pk; }
+    return pk;
+}
+
+// Balanced part of the exact re-check, run by one whole warp, out of line (it only runs for warps in which some row has more than one
+// in-band group, and must not cost the main path registers).  The rows' first groups are done by the caller (lane = row); the remaining
+// (row, group) pairs are flattened level by level (level k = the rows that have a k-th group, k >= 1) and dealt out evenly, one
+// (group, column) per lane and staging buffer, so a warp does not need as many rounds as its busiest lane.  Per-row maxima meet in
+// bestS (shared-memory atom.max on the packed key).  n = this lane's group count, glist_col = &glist[0][tile row of lane 0] (row stride
+// TC_BM), ownS = the warp's 32 staged own rows (XOR-swizzled float4 chunks), stage = 4 staging buffers of 32 rows.
+template <bool COLDIR>
+__device__ __noinline__ void warp_recheck_balanced(int n, int nmax, const uint32_t* glist_col, const float4* ownS, float4* stage, unsigned long long* bestS,
+                                                   float own_hn, const float* __restrict__ xs, const float* hn_smem, int col0, int j_end)
+{
+    const int lane = threadIdx.x & 31, sub = lane >> 3, chunk = lane & 7;
+    int total = 0;                                                    // groups beyond the first, over the whole warp
+    for (int kk = 1; kk < nmax; ++kk) total += __popc(__ballot_sync(0xffffffffu, n > kk));
+    for (int base = 0; base < TC_SUB * total; base += TC_SUB * 32) {
+        int jc[TC_SUB], rl[TC_SUB];
+        float4 reg[TC_SUB][8];
+#pragma unroll
+        for (int u = 0; u < TC_SUB; ++u) {
+            const int item = base + u * 32 + lane;
+            int rem = item >> 2, src = -1, kf = 0;                   // item -> (level kf, rem-th row of that level, column item & 3)
+            for (int kk = 1; kk < nmax; ++kk) {
+                unsigned m = __ballot_sync(0xffffffffu, n > kk);
+                const int cnt = __popc(m);
+                if (src < 0) {
+                    if (rem < cnt) { for (int q2 = 0; q2 < rem; ++q2) m &= m - 1u; src = __ffs((int)m) - 1; kf = kk; }
+                    else rem -= cnt;
+                }
+            }
+            const int j0 = (src >= 0) ? (int)glist_col[kf * TC_BM + src] : -0x40000000;
+            jc[u] = (j0 >= 0 && j0 + (item & 3) < j_end) ? j0 + (item & 3) : -1;
+            rl[u] = src >= 0 ? src : 0;
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) {                          // cooperative gather: 8 lanes per 128-byte row, 4 rows per instruction
+                const int jr = __shfl_sync(0xffffffffu, jc[u], 4 * s8 + sub);
+                reg[u][s8] = (jr >= 0) ? __ldg(reinterpret_cast<const float4*>(xs + (size_t)jr * TC_D) + chunk) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < TC_SUB; ++u)
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) { const int rid = 4 * s8 + sub; stage[u * 256 + rid * 8 + (chunk ^ (rid & 7))] = reg[u][s8]; }
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < TC_SUB; ++u) {
+            const float ohn = __shfl_sync(0xffffffffu, own_hn, rl[u]);
+            if (jc[u] >= 0) {
+                const float cand_hn = hn_smem[jc[u] - col0];
+                float acc = COLDIR ? ohn : cand_hn;
+#pragma unroll
+                for (int k4 = 0; k4 < 8; ++k4) {
+                    const float4 o = ownS[rl[u] * 8 + (k4 ^ (rl[u] & 7))], c = stage[u * 256 + lane * 8 + (k4 ^ (lane & 7))];
+                    acc = __fmaf_rn(o.x, c.x, acc); acc = __fmaf_rn(o.y, c.y, acc); acc = __fmaf_rn(o.z, c.z, acc); acc = __fmaf_rn(o.w, c.w, acc);
+                }
+                const float e = COLDIR ? __fadd_rn(acc, cand_hn) : acc;
+                atomicMax(&bestS[rl[u]], pack_best(float_key(e), (uint32_t)jc[u]));
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <bool COLDIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant__ CUtensorMap map_str,
@@ -386,7 +470,6 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             const float thr = m_run - band;
             bool overflow = dropped_max >= thr;                       // a dropped event could still hold the maximum: exact scan of the row
             const int j_end = min(N, t_end * TC_BN);
-            float best = -INFINITY; int best_j = 0x7fffffff;
             const int sub = lane >> 3, chunk = lane & 7;
             // gather 32 rows (one per lane, row index `want`, -1 = none) of `base` into registers, 4 rows per instruction
             auto fetch = [&](const float* __restrict__ base, int want, float4 (&reg)[8]) {
@@ -436,13 +519,12 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                 for (int c = 0; c < 8; ++c) rowv[c] = stage[buf * 256 + lane * 8 + (c ^ (lane & 7))];
             };
             // own rows: staged once per warp in operand memory that is dead by now (the bf16 own tile / the third TMA stage), so that any
-            // lane can read any row of the warp in the balanced part below
+            // lane can score any row of the warp in the balanced part and in the overflow scan
             float4* ownS = (ew < 4) ? reinterpret_cast<float4*>(sm.a) + ew * 256 : reinterpret_cast<float4*>(sm.b[2]) + (ew - 4) * 256;
-            unsigned long long* bestS = reinterpret_cast<unsigned long long*>(stage + TC_SUB * 256);      // per-row maxima of the balanced part
+            unsigned long long* bestS = reinterpret_cast<unsigned long long*>(stage + TC_SUB * 256);      // per-row maxima (packed)
             float4 own[8];
 #pragma unroll
             for (int s8 = 0; s8 < 8; ++s8) { const int rid = 4 * s8 + sub; ownS[rid * 8 + (chunk ^ (rid & 7))] = reg[0][s8]; }
-            bestS[lane] = 0ull;
             __syncwarp();
 #pragma unroll
             for (int c = 0; c < 8; ++c) own[c] = ownS[lane * 8 + (c ^ (lane & 7))];
@@ -451,20 +533,8 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             tv_own = clock64(); tv_rounds = nmax;
 #endif
             const float* xs = x_str + (size_t)os * TC_D;
-            // exact score of (own row values o, its half-norm ohn) against streamed column j whose row is in staging buffer `buf`
-            auto exact_staged = [&](const float4 (&o)[8], float ohn, int buf, int j) -> float {
-                float4 c[8];
-                get(buf, c);
-                const float cand_hn = sm.hn[j - t_begin * TC_BN];
-                float acc = COLDIR ? ohn : cand_hn;
-#pragma unroll
-                for (int k4 = 0; k4 < 8; ++k4) {
-                    acc = __fmaf_rn(o[k4].x, c[k4].x, acc); acc = __fmaf_rn(o[k4].y, c[k4].y, acc);
-                    acc = __fmaf_rn(o[k4].z, c[k4].z, acc); acc = __fmaf_rn(o[k4].w, c[k4].w, acc);
-                }
-                return COLDIR ? __fadd_rn(acc, cand_hn) : acc;
-            };
-            // first group of every row: lane = row, the four columns of the group in one memory round trip
+            float best = -INFINITY; int best_j = 0x7fffffff;
+            // first group of every row: lane = row, the four columns of the group in one memory round trip (the common case ends here)
             if (nmax > 0) {
                 const int j0 = (n > 0) ? (int)glist[0][r] : -0x40000000;
                 int jc[TC_SUB];
@@ -482,77 +552,36 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
 #pragma unroll
                 for (int u = 0; u < TC_SUB; ++u) {
                     if (jc[u] >= 0) {
-                        const float e = exact_staged(own, own_hn, u, jc[u]);
+                        float4 c[8];
+                        get(u, c);
+                        const float cand_hn = sm.hn[jc[u] - t_begin * TC_BN];
+                        float acc = COLDIR ? own_hn : cand_hn;
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; ++k4) {
+                            acc = __fmaf_rn(own[k4].x, c[k4].x, acc); acc = __fmaf_rn(own[k4].y, c[k4].y, acc);
+                            acc = __fmaf_rn(own[k4].z, c[k4].z, acc); acc = __fmaf_rn(own[k4].w, c[k4].w, acc);
+                        }
+                        const float e = COLDIR ? __fadd_rn(acc, cand_hn) : acc;
                         if (e > best || (e == best && jc[u] < best_j)) { best = e; best_j = jc[u]; }
                     }
                 }
                 __syncwarp();
             }
-            // further groups (rows without a clear winner have a few): a warp would need as many rounds as its busiest lane, so the
-            // remaining (row, group) items are flattened level by level (level k = the rows that have a k-th group) and dealt out evenly,
-            // one (group, column) per lane and staging buffer; per-row maxima meet in shared memory (atom.max on the packed key)
-            if (nmax > 1) {
-                int total = 0;
-                for (int kk = 1; kk < nmax; ++kk) total += __popc(__ballot_sync(0xffffffffu, n > kk));
-                const int rbase = r - lane;                           // tile row of lane 0
-                for (int base = 0; base < TC_SUB * total; base += TC_SUB * 32) {
-                    int jc[TC_SUB], rl[TC_SUB];
-#pragma unroll
-                    for (int u = 0; u < TC_SUB; ++u) {
-                        const int item = base + u * 32 + lane;
-                        int rem = item >> 2, src = -1, kf = 0;       // item -> (level kf, rem-th row of that level)
-                        for (int kk = 1; kk < nmax; ++kk) {
-                            unsigned m = __ballot_sync(0xffffffffu, n > kk);
-                            const int cnt = __popc(m);
-                            if (src < 0) {
-                                if (rem < cnt) { for (int q2 = 0; q2 < rem; ++q2) m &= m - 1u; src = __ffs((int)m) - 1; kf = kk; }
-                                else rem -= cnt;
-                            }
-                        }
-                        const int j0 = (src >= 0) ? (int)glist[kf][rbase + src] : -0x40000000;
-                        jc[u] = (j0 >= 0 && j0 + (item & 3) < j_end) ? j0 + (item & 3) : -1;
-                        rl[u] = src >= 0 ? src : 0;
-                        fetch(xs, jc[u], reg[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < TC_SUB; ++u) put(u, reg[u]);
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < TC_SUB; ++u) {
-                        const float ohn = __shfl_sync(0xffffffffu, own_hn, rl[u]);
-                        if (jc[u] >= 0) {
-                            float4 o[8];
-#pragma unroll
-                            for (int c = 0; c < 8; ++c) o[c] = ownS[rl[u] * 8 + (c ^ (rl[u] & 7))];
-                            const float e = exact_staged(o, ohn, u, jc[u]);
-                            atomicMax(&bestS[rl[u]], pack_best(float_key(e), (uint32_t)jc[u]));
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
+            bestS[lane] = (best_j != 0x7fffffff) ? pack_best(float_key(best), (uint32_t)best_j) : 0ull;
+            __syncwarp();
+            if (nmax > 1)                                             // rows without a clear winner: their further groups, dealt out evenly
+                warp_recheck_balanced<COLDIR>(n, nmax, &glist[0][r - lane], ownS, stage, bestS, own_hn, xs, sm.hn, t_begin * TC_BN, j_end);
+            __syncwarp();
             // pathological rows (an in-band event had to be dropped: many near-duplicates, or ten chunks within the band of the maximum): exact
             // scan of the row, done by the whole warp (lane l takes columns l, l + 32, ...) - a single lane would hold its SM for milliseconds
             unsigned long long scan_best = 0ull;
             for (unsigned ovm = __ballot_sync(0xffffffffu, valid && overflow); ovm; ovm &= ovm - 1u) {
                 const int src = __ffs((int)ovm) - 1;
-                float4 o[8];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) o[c] = ownS[src * 8 + (c ^ (src & 7))];
                 const float ohn = __shfl_sync(0xffffffffu, own_hn, src);
-                float sb = -INFINITY; int sj = 0x7fffffff;
-#pragma unroll 2
-                for (int j = t_begin * TC_BN + lane; j < j_end; j += 32) {
-                    const float e = exact_score<COLDIR>(o, ohn, xs + (size_t)j * TC_D, hn_str_p[j]);
-                    if (e > sb) { sb = e; sj = j; }                   // ascending j per lane: strict > keeps the lowest index
-                }
-                unsigned long long pk = (sj != 0x7fffffff) ? pack_best(float_key(sb), (uint32_t)sj) : 0ull;
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, pk, off); pk = other > pk ? other : pk; }
+                const unsigned long long pk = warp_exact_scan<COLDIR>(ownS + src * 8, src & 7, ohn, xs, hn_str_p, t_begin * TC_BN, j_end);
                 if (lane == src) scan_best = pk;
             }
-            unsigned long long fin = (best_j != 0x7fffffff) ? pack_best(float_key(best), (uint32_t)best_j) : 0ull;
-            if (nmax > 1) { const unsigned long long other = bestS[lane]; fin = other > fin ? other : fin; }
+            unsigned long long fin = bestS[lane];
             fin = scan_best > fin ? scan_best : fin;
             if (valid && fin != 0ull) red_max_u64(out_packed + (size_t)p * pad_own + row, fin);
         }

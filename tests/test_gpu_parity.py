@@ -389,3 +389,43 @@ def test_config5_huge_pair_split_by_hypothesis(oracle, backend):
     Tr, it, _ = backend.post_refinement_batched(T, rm["corr"], off, cnt, 0.1)
     recall, rte, rre = S.registration_recall(Tr.cpu(), b.T_gt.cpu())
     assert recall == 1.0 and int(inl) > 29000 and float(rte.max()) < 1e-3
+
+
+@pytest.mark.gpu
+def test_tensor_filter_equals_fp32_kernel_on_stress_inputs(backend):
+    """the tensor-core filter path against the all-FP32 kernel (itself bit-exact with the oracle above) on inputs built to stress the exact
+    re-check: clusters of near-duplicates (several in-band groups per row -> balanced passes), a dense blob (candidate-list overflow ->
+    warp-cooperative scan), unrelated rows, un-normalised rows with duplicates and zeros, ragged sizes, column splits (N > 6144)"""
+    g = torch.Generator().manual_seed(4242)
+    nrm = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    r = lambda *s: torch.randn(*s, generator=g)
+
+    def make(kind, M, N):
+        if kind == "unrelated":
+            return nrm(r(M, 32)), nrm(r(N, 32))
+        if kind == "clusters":
+            nc = max(1, N // 9); centers = nrm(r(nc, 32))
+            tgt = nrm(centers[torch.randint(0, nc, (N,), generator=g)] + (10.0 ** torch.empty(N, 1).uniform_(-5, -2, generator=g)) * r(N, 32))
+            return nrm(centers[torch.randint(0, nc, (M,), generator=g)] + 0.02 * r(M, 32)), tgt
+        if kind == "flood":
+            c = nrm(r(1, 32))
+            return nrm(c + 1e-3 * r(M, 32)), torch.cat([nrm(c + 1e-4 * r(N // 2, 32)), nrm(r(N - N // 2, 32))])
+        src = r(M, 32) * 10.0 ** torch.empty(M, 1).uniform_(-2, 2, generator=g)          # "scaled"
+        tgt = r(N, 32) * 10.0 ** torch.empty(N, 1).uniform_(-2, 2, generator=g)
+        tgt[::11] = tgt[1::11][: tgt[::11].shape[0]]; src[::13] = 0.0
+        return src, tgt
+
+    cases = [("unrelated", 5000, 5000), ("clusters", 3100, 2900), ("flood", 1500, 2600), ("scaled", 2222, 3333), ("clusters", 700, 9000),
+             ("unrelated", 257, 12500), ("flood", 300, 700), ("clusters", 4999, 513)]
+    try:
+        for kind, M, N in cases:
+            src, tgt = make(kind, M, N)
+            src, tgt = src.to(DEV), tgt.to(DEV)
+            out = {}
+            for algo in (backend.K1_FP32, backend.K1_TENSOR_FILTER):
+                backend.set_k1_algo(algo)
+                out[algo] = backend.mutual_matching_device(src, tgt, want_dist=True)
+            for key in ("nn_s", "nn_t", "dist_s", "dist_t"):
+                assert torch.equal(out[backend.K1_FP32][key], out[backend.K1_TENSOR_FILTER][key]), (kind, M, N, key)
+    finally:
+        backend.set_k1_algo(backend.K1_TENSOR_FILTER)

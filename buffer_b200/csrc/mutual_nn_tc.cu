@@ -279,10 +279,16 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     float hmin = 0.0f, hmax = -INFINITY;
-    for (int i = threadIdx.x; i < ntiles * TC_BN; i += TC_THREADS) {
-        const float h = hn_str_p[t_begin * TC_BN + i];               // padded array: -inf beyond N
-        sm.hn[i] = h;
-        if (h > -INFINITY) { hmin = fminf(hmin, h); hmax = fmaxf(hmax, h); }
+    {   // 128-bit loads: the tile range starts on a 1 KB boundary of the padded array (-inf beyond N)
+        const float4* src4 = reinterpret_cast<const float4*>(hn_str_p + (size_t)t_begin * TC_BN);
+        float4* dst4 = reinterpret_cast<float4*>(sm.hn);
+        for (int i = threadIdx.x; i < ntiles * (TC_BN / 4); i += TC_THREADS) {
+            const float4 h = __ldg(src4 + i);
+            dst4[i] = h;
+            const float hv[4] = { h.x, h.y, h.z, h.w };
+#pragma unroll
+            for (int c = 0; c < 4; ++c) if (hv[c] > -INFINITY) { hmin = fminf(hmin, hv[c]); hmax = fmaxf(hmax, hv[c]); }
+        }
     }
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) { hmin = fminf(hmin, __shfl_xor_sync(0xffffffffu, hmin, o)); hmax = fmaxf(hmax, __shfl_xor_sync(0xffffffffu, hmax, o)); }

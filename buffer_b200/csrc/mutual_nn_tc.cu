@@ -89,6 +89,11 @@ BFR_DEVINL void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, u
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+// asynchronous L2 prefetch of a contiguous global range (bytes % 16 == 0, 16-byte aligned)
+BFR_DEVINL void l2_prefetch(const void* gptr, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 BFR_DEVINL uint64_t umma_desc_sw64(const void* smem)
 {   // K-major, SWIZZLE_64B: 8-row groups 512 B apart (SBO = 32 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell), layout 4 = SW64
     return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
@@ -310,6 +315,19 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         if (lane == 0) {
             mbar_expect_tx(&sm.a_full, TC_BM * TC_D * 2);
             tma_load_2d(sm.a, &map_own, 0, oo + row0, &sm.a_full);
+#ifndef TC_NO_L2_PREFETCH
+            // The exact re-check reads FP32 rows the main loop never touches (it streams the bf16 copies): the CTA's own rows and a
+            // scattered subset of the streamed set.  Pull them towards L2 now - the own rows, and this CTA's share of the streamed rows of
+            // the pair (together the row blocks of a pair cover all of them) - so that the re-check waits for L2, not for DRAM.
+            {
+                const int own_rows = min(TC_BM, M - row0);
+                l2_prefetch(x_own + (size_t)(oo + row0) * TC_D, (uint32_t)own_rows * TC_D * 4u);
+                const int nblk = (int)gridDim.x, j0 = t_begin * TC_BN, j1 = min(N, t_end * TC_BN);
+                const int per = ((j1 - j0 + nblk - 1) / nblk + 7) & ~7;                      // rows per row block, rounded to 1 KB
+                const int a0 = j0 + (int)blockIdx.x * per, a1 = min(j1, a0 + per);
+                if (a1 > a0) l2_prefetch(x_str + (size_t)(os + a0) * TC_D, (uint32_t)(a1 - a0) * TC_D * 4u);
+            }
+#endif
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(&sm.empty[s], ph ^ 1u);

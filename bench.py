@@ -305,7 +305,7 @@ def main():
                "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gbs": sum(x.numel() * 4 for x in h) / (h2d_ms * 1e-3) * 1e-9,
                "h2d_bytes_per_step": int(sum(x.numel() * 4 for x in h)), "d2h_bytes_per_step": int(Th.numel() * 4 + nmh.numel() * 4 + nih.numel() * 4),
                "api": "buffer_b200.backend.HostRegistrar.run -> bfr_register_uniform_host (pinned host buffers, %d-pair chunks on 2 streams)" % chunk,
-               "poses_equal_device_path": same, "launches_per_step": (9 if args.k1_algo == 1 else 8) * ((P + chunk - 1) // chunk)}
+               "poses_equal_device_path": same, "launches_per_step": 8 * ((P + chunk - 1) // chunk)}
 
     if rank == 0:
         flops_k1 = 2.0 * N * N * 32 * P
@@ -329,7 +329,7 @@ def main():
             # the pipe drains on every switch to another accumulator tile, ~345 cycles per tile whatever its N (profiles/r01_mma_pipeline_microbench.txt)
             tiles = 2.0 * P * ((N + 127) // 128) * ((N + 255) // 256)
             mma_floor_ms = tiles / 148.0 * 345.0 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)
-            roof = {"kernel": "k1_tc_kernel x2 (tcgen05 bf16 filter, 128x256 accumulator tiles in TMEM + exact FP32 re-check; src->tgt and tgt->src)", "bound": "tensor",
+            roof = {"kernel": "k1_tc_kernel (one launch, both directions: tcgen05 bf16 filter, 128x256 accumulator tiles in TMEM + exact FP32 re-check)", "bound": "tensor",
                     "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": traffic,
                     "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step, "algorithmic_flops_per_launch": flops_k1,
                     "executed_tensor_flops_per_launch": 2 * flops_k1,
@@ -343,7 +343,7 @@ def main():
             roof = dict(fp32_roof, traffic=traffic, k1_ms_per_launch=k1_ms, k1_share_of_step=k1_ms / ms_step, algorithmic_flops_per_launch=flops_k1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args, c, P), "clocks": clocks, "gpu_launches": (8 if args.k1_algo == 1 else 7) * args.steps,
+                "config": config_dict(args, c, P), "clocks": clocks, "gpu_launches": 7 * args.steps,
                 "roofline": roof, "roofline_fp32_path": fp32_roof,
                 "roofline_ransac": {"kernel": "ransac_kernel (Philox + Kabsch + checkers + inlier scoring)", "bound": "fp32", "ms_per_launch": ransac_ms,
                                     "valid_hypotheses_per_pair": hv_total / P, "hypotheses_per_pair": c["hypotheses"], "correspondences_per_pair": c_mean,

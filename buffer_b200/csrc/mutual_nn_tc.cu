@@ -141,8 +141,7 @@ BFR_DEVINL void tmem_ld_pin(float (&v)[32])
 }
 
 // exact score of (own row, candidate row) — the oracle's chain.  COLDIR = the "own" side is the target set.
-template <bool COLDIR>
-BFR_DEVINL float exact_score(const float4 (&own)[8], float own_hn, const float* __restrict__ cand_row, float cand_hn)
+BFR_DEVINL float exact_score(bool COLDIR, const float4 (&own)[8], float own_hn, const float* __restrict__ cand_row, float cand_hn)
 {
     float acc = COLDIR ? own_hn : cand_hn;
     const float4* c4 = reinterpret_cast<const float4*>(cand_row);
@@ -158,8 +157,7 @@ BFR_DEVINL float exact_score(const float4 (&own)[8], float own_hn, const float* 
 // exact scan of one row by a whole warp (lane l takes streamed columns j_begin + l, + 32, ...): the fallback for rows whose candidate list
 // overflowed.  `o` = the own row (every lane holds the same values), returns the packed best (key << 32 | ~index) in every lane.  Kept out of
 // line: it runs for a handful of rows per launch and must not cost the main path registers or instruction-cache lines.
-template <bool COLDIR>
-__device__ __noinline__ unsigned long long warp_exact_scan(const float4* __restrict__ own_row_smem, int swz, float ohn, const float* __restrict__ xs,
+__device__ __noinline__ unsigned long long warp_exact_scan(bool COLDIR, const float4* __restrict__ own_row_smem, int swz, float ohn, const float* __restrict__ xs,
                                                            const float* __restrict__ hn_str_p, int j_begin, int j_end)
 {
     const int lane = threadIdx.x & 31;
@@ -169,7 +167,7 @@ __device__ __noinline__ unsigned long long warp_exact_scan(const float4* __restr
     float sb = -INFINITY; int sj = 0x7fffffff;
 #pragma unroll 2
     for (int j = j_begin + lane; j < j_end; j += 32) {
-        const float e = exact_score<COLDIR>(o, ohn, xs + (size_t)j * TC_D, hn_str_p[j]);
+        const float e = exact_score(COLDIR, o, ohn, xs + (size_t)j * TC_D, hn_str_p[j]);
         if (e > sb) { sb = e; sj = j; }                               // ascending j per lane: strict > keeps the lowest index
     }
     unsigned long long pk = (sj != 0x7fffffff) ? pack_best(float_key(sb), (uint32_t)sj) : 0ull;
@@ -184,8 +182,7 @@ __device__ __noinline__ unsigned long long warp_exact_scan(const float4* __restr
 // (group, column) per lane and staging buffer, so a warp does not need as many rounds as its busiest lane.  Per-row maxima meet in
 // bestS (shared-memory atom.max on the packed key).  n = this lane's group count, glist_col = &glist[0][tile row of lane 0] (row stride
 // TC_BM), ownS = the warp's 32 staged own rows (XOR-swizzled float4 chunks), stage = 4 staging buffers of 32 rows.
-template <bool COLDIR>
-__device__ __noinline__ void warp_recheck_balanced(int n, int nmax, const uint32_t* glist_col, const float4* ownS, float4* stage, unsigned long long* bestS,
+__device__ __noinline__ void warp_recheck_balanced(bool COLDIR, int n, int nmax, const uint32_t* glist_col, const float4* ownS, float4* stage, unsigned long long* bestS,
                                                    float own_hn, const float* __restrict__ xs, const float* hn_smem, int col0, int j_end)
 {
     const int lane = threadIdx.x & 31, sub = lane >> 3, chunk = lane & 7;
@@ -239,22 +236,41 @@ __device__ __noinline__ void warp_recheck_balanced(int n, int nmax, const uint32
     }
 }
 
-template <bool COLDIR>
+// One launch covers both directions of every pair: row blocks [0, nblk_src) of a pair own source rows and stream the target set
+// (-> row_packed), row blocks [nblk_src, gridDim.x) own target rows and stream the source set (-> col_packed).  The CTAs of a pair are
+// adjacent in launch order, so the second direction finds the pair's descriptors (FP32 and bf16) in L2.
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant__ CUtensorMap map_str,
-             const float* __restrict__ x_own, const float* __restrict__ x_str,
-             const int32_t* __restrict__ off_own, const int32_t* __restrict__ off_str,
-             const float* __restrict__ hn_own, const float* __restrict__ hn_str, int pad_own, int pad_str,
-             unsigned long long* __restrict__ out_packed, int splits)
+k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_constant__ CUtensorMap map_tgt_str,
+             const __grid_constant__ CUtensorMap map_tgt_own, const __grid_constant__ CUtensorMap map_src_str,
+             const float* __restrict__ src, const float* __restrict__ tgt,
+             const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
+             const float* __restrict__ hn_src, const float* __restrict__ hn_tgt, int pad_src, int pad_tgt,
+             unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_packed,
+             int nblk_src, int splits_src, int splits_tgt)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];      // no static shared memory in this kernel: base is 1024-aligned
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
     if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();                 // swizzle atoms need (at least) 512-byte alignment
 
+    const bool COLDIR = (int)blockIdx.x >= nblk_src;                  // the "own" side is the target set
+    const int bx = (int)blockIdx.x - (COLDIR ? nblk_src : 0), nbx = COLDIR ? (int)gridDim.x - nblk_src : nblk_src;
+    const int splits = COLDIR ? splits_tgt : splits_src;
+    if ((int)blockIdx.y >= splits) return;
+    const CUtensorMap* map_own = COLDIR ? &map_tgt_own : &map_src_own;
+    const CUtensorMap* map_str = COLDIR ? &map_src_str : &map_tgt_str;
+    const float* __restrict__ x_own = COLDIR ? tgt : src;
+    const float* __restrict__ x_str = COLDIR ? src : tgt;
+    const int32_t* __restrict__ off_own = COLDIR ? tgt_off : src_off;
+    const int32_t* __restrict__ off_str = COLDIR ? src_off : tgt_off;
+    const float* __restrict__ hn_own = COLDIR ? hn_tgt : hn_src;
+    const float* __restrict__ hn_str = COLDIR ? hn_src : hn_tgt;
+    const int pad_own = COLDIR ? pad_tgt : pad_src, pad_str = COLDIR ? pad_src : pad_tgt;
+    unsigned long long* __restrict__ out_packed = COLDIR ? col_packed : row_packed;
+
     const int p = blockIdx.z;
     const int oo = off_own[p], M = off_own[p + 1] - oo;
     const int os = off_str[p], N = off_str[p + 1] - os;
-    const int row0 = blockIdx.x * TC_BM;
+    const int row0 = bx * TC_BM;
     if (row0 >= M || N <= 0) return;
     const int ntiles_all = (N + TC_BN - 1) / TC_BN;
     const int t_begin = (int)(((long long)blockIdx.y * ntiles_all) / splits);
@@ -314,7 +330,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
         // ================= TMA producer =================
         if (lane == 0) {
             mbar_expect_tx(&sm.a_full, TC_BM * TC_D * 2);
-            tma_load_2d(sm.a, &map_own, 0, oo + row0, &sm.a_full);
+            tma_load_2d(sm.a, map_own, 0, oo + row0, &sm.a_full);
 #ifndef TC_NO_L2_PREFETCH
             // The exact re-check reads FP32 rows the main loop never touches (it streams the bf16 copies): the CTA's own rows and a
             // scattered subset of the streamed set.  Pull them towards L2 now - the own rows, and this CTA's share of the streamed rows of
@@ -322,9 +338,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             {
                 const int own_rows = min(TC_BM, M - row0);
                 l2_prefetch(x_own + (size_t)(oo + row0) * TC_D, (uint32_t)own_rows * TC_D * 4u);
-                const int nblk = (int)gridDim.x, j0 = t_begin * TC_BN, j1 = min(N, t_end * TC_BN);
+                const int nblk = nbx, j0 = t_begin * TC_BN, j1 = min(N, t_end * TC_BN);
                 const int per = ((j1 - j0 + nblk - 1) / nblk + 7) & ~7;                      // rows per row block, rounded to 1 KB
-                const int a0 = j0 + (int)blockIdx.x * per, a1 = min(j1, a0 + per);
+                const int a0 = j0 + bx * per, a1 = min(j1, a0 + per);
                 if (a1 > a0) l2_prefetch(x_str + (size_t)(os + a0) * TC_D, (uint32_t)(a1 - a0) * TC_D * 4u);
             }
 #endif
@@ -332,7 +348,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(&sm.empty[s], ph ^ 1u);
                 mbar_expect_tx(&sm.full[s], TC_BN * TC_D * 2);
-                tma_load_2d(sm.b[s], &map_str, 0, os + (t_begin + it) * TC_BN, &sm.full[s]);
+                tma_load_2d(sm.b[s], map_str, 0, os + (t_begin + it) * TC_BN, &sm.full[s]);
             }
         }
     } else if (warp == 1) {
@@ -594,7 +610,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             bestS[lane] = (best_j != 0x7fffffff) ? pack_best(float_key(best), (uint32_t)best_j) : 0ull;
             __syncwarp();
             if (nmax > 1)                                             // rows without a clear winner: their further groups, dealt out evenly
-                warp_recheck_balanced<COLDIR>(n, nmax, &glist[0][r - lane], ownS, stage, bestS, own_hn, xs, sm.hn, t_begin * TC_BN, j_end);
+                warp_recheck_balanced(COLDIR, n, nmax, &glist[0][r - lane], ownS, stage, bestS, own_hn, xs, sm.hn, t_begin * TC_BN, j_end);
             __syncwarp();
             // pathological rows (an in-band event had to be dropped: many near-duplicates, or ten chunks within the band of the maximum): exact
             // scan of the row, done by the whole warp (lane l takes columns l, l + 32, ...) - a single lane would hold its SM for milliseconds
@@ -602,7 +618,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
             for (unsigned ovm = __ballot_sync(0xffffffffu, valid && overflow); ovm; ovm &= ovm - 1u) {
                 const int src = __ffs((int)ovm) - 1;
                 const float ohn = __shfl_sync(0xffffffffu, own_hn, src);
-                const unsigned long long pk = warp_exact_scan<COLDIR>(ownS + src * 8, src & 7, ohn, xs, hn_str_p, t_begin * TC_BN, j_end);
+                const unsigned long long pk = warp_exact_scan(COLDIR, ownS + src * 8, src & 7, ohn, xs, hn_str_p, t_begin * TC_BN, j_end);
                 if (lane == src) scan_best = pk;
             }
             unsigned long long fin = bestS[lane];
@@ -618,7 +634,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_own, const __grid_constant_
     __syncthreads();
 #ifdef TC_TIMING
     tq4 = clock64();
-    if (blockIdx.z == 3 && blockIdx.x == 1 && lane == 0 && (warp == 2 || warp == 9)) printf("dir %d cta %d warp %d: setup %lld main %lld (acc wait %lld ldwait %lld proc %lld compact %lld) verify %lld (glist %lld own %lld nmax %lld loadwait %lld) tailwait %lld\n", (int)COLDIR, blockIdx.x, warp, tq1 - tq0, tq2 - tq1, tq_wait, tq_ld, tq_proc, tq_cmp, tq3 - tq2, tv_glist - tq2, tv_own - tv_glist, tv_rounds, tv_lat, tq4 - tq3);
+    if (blockIdx.z == 3 && bx == 1 && lane == 0 && (warp == 2 || warp == 9)) printf("dir %d cta %d warp %d: setup %lld main %lld (acc wait %lld ldwait %lld proc %lld compact %lld) verify %lld (glist %lld own %lld nmax %lld loadwait %lld) tailwait %lld\n", (int)COLDIR, bx, warp, tq1 - tq0, tq2 - tq1, tq_wait, tq_ld, tq_proc, tq_cmp, tq3 - tq2, tv_glist - tq2, tv_own - tv_glist, tv_rounds, tv_lat, tq4 - tq3);
 #endif
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
 }
@@ -668,21 +684,19 @@ cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_bf1
     const size_t smem = sizeof(TcSmem) + 1024;
     static bool once = false;
     if (!once) {
-        cudaError_t e = cudaFuncSetAttribute(k1_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(k1_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(k1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         once = true;
     }
-    {   // src rows own, tgt streamed -> row_packed
-        const int tiles = (max_N + TC_BN - 1) / TC_BN, splits = (tiles + TC_MAX_TILES - 1) / TC_MAX_TILES;
-        dim3 grid((unsigned)((max_M + TC_BM - 1) / TC_BM), (unsigned)(splits > 0 ? splits : 1), (unsigned)P);
-        k1_tc_kernel<false><<<grid, TC_THREADS, smem, stream>>>(ms_own, mt_str, src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, (int)grid.y);
-    }
-    {   // tgt rows own, src streamed -> col_packed
-        const int tiles = (max_M + TC_BN - 1) / TC_BN, splits = (tiles + TC_MAX_TILES - 1) / TC_MAX_TILES;
-        dim3 grid((unsigned)((max_N + TC_BM - 1) / TC_BM), (unsigned)(splits > 0 ? splits : 1), (unsigned)P);
-        k1_tc_kernel<true><<<grid, TC_THREADS, smem, stream>>>(mt_own, ms_str, tgt, src, tgt_off, src_off, hnb, hna, padN, padM, col_packed, (int)grid.y);
-    }
+    // one launch, both directions: x = row blocks of the source side, then of the target side; y = column splits (the larger of the two
+    // directions' counts; the other direction's surplus CTAs exit at once); z = pair
+    const int nblk_src = (max_M + TC_BM - 1) / TC_BM, nblk_tgt = (max_N + TC_BM - 1) / TC_BM;
+    const int tiles_tgt = (max_N + TC_BN - 1) / TC_BN, tiles_src = (max_M + TC_BN - 1) / TC_BN;
+    const int splits_src = (tiles_tgt + TC_MAX_TILES - 1) / TC_MAX_TILES > 0 ? (tiles_tgt + TC_MAX_TILES - 1) / TC_MAX_TILES : 1;   // src rows own, tgt streamed
+    const int splits_tgt = (tiles_src + TC_MAX_TILES - 1) / TC_MAX_TILES > 0 ? (tiles_src + TC_MAX_TILES - 1) / TC_MAX_TILES : 1;   // tgt rows own, src streamed
+    dim3 grid((unsigned)(nblk_src + nblk_tgt), (unsigned)(splits_src > splits_tgt ? splits_src : splits_tgt), (unsigned)P);
+    k1_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(ms_own, mt_str, mt_own, ms_str, src, tgt, src_off, tgt_off, hna, hnb, padM, padN,
+                                                     row_packed, col_packed, nblk_src, splits_src, splits_tgt);
     return cudaGetLastError();
 }
 

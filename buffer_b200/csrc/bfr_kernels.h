@@ -12,7 +12,7 @@ size_t k1_workspace_bytes(int P, int max_M, int max_N);
 void k1_set_algo(int algo);
 int k1_get_algo();
 bool k1_tc_supported(int D, long long total_M, long long total_N);
-cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_bf16, const void* tgt_bf16, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_f16, const void* tgt_f16, const int32_t* out_of_range, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
                          long long total_M, long long total_N, const float* hna, const float* hnb, int padM, int padN,
                          unsigned long long* row_packed, unsigned long long* col_packed, cudaStream_t stream);
 cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,

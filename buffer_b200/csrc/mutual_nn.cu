@@ -39,9 +39,11 @@ struct __align__(128) K1Smem {
 };
 
 // ---- prep: half squared norms into the padded workspace (-inf in the padding), zeroed packed bests and -- for the tensor-core
-// path -- a bf16 (round-to-nearest-even) copy of the descriptors, row o + i of the concatenated array -> row o + i of xb ----------
+// path -- an f16 (round-to-nearest-even) copy of the descriptors, row o + i of the concatenated array -> row o + i of xb.  A pair with an
+// element that f16 cannot hold (|x| > 65504 or non-finite) is flagged in oor[p]: the tensor-core kernel then scans that pair exactly ------
 __global__ void __launch_bounds__(256) k1_prep_kernel(const float* __restrict__ x, const int32_t* __restrict__ off, int P, int D, int pad,
-                                                      float* __restrict__ hn, unsigned long long* __restrict__ packed, uint4* __restrict__ xb)
+                                                      float* __restrict__ hn, unsigned long long* __restrict__ packed, uint4* __restrict__ xb,
+                                                      int32_t* __restrict__ oor)
 {
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)P * pad) return;
@@ -60,14 +62,18 @@ __global__ void __launch_bounds__(256) k1_prep_kernel(const float* __restrict__ 
                 s = __fmaf_rn(v[k].x, v[k].x, s); s = __fmaf_rn(v[k].y, v[k].y, s); s = __fmaf_rn(v[k].z, v[k].z, s); s = __fmaf_rn(v[k].w, v[k].w, s);
             }
             if (xb) {
+                float amax = 0.0f;
+#pragma unroll
+                for (int k = 0; k < K1_D / 4; ++k) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v[k].x), fabsf(v[k].y)), fmaxf(fabsf(v[k].z), fabsf(v[k].w))));
+                if (!(amax <= 65504.0f) || !(s == s)) atomicOr(&oor[p], 1);                  // (NaN elements: fmaxf drops them, the norm does not)
                 uint4* dst = xb + (size_t)(o + i) * (K1_D / 8);
 #pragma unroll
                 for (int k = 0; k < K1_D / 8; ++k) {
                     uint4 w;
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v[2 * k].y), "f"(v[2 * k].x));       // low half = first element
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v[2 * k].w), "f"(v[2 * k].z));
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.z) : "f"(v[2 * k + 1].y), "f"(v[2 * k + 1].x));
-                    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w.w) : "f"(v[2 * k + 1].w), "f"(v[2 * k + 1].z));
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w.x) : "f"(v[2 * k].y), "f"(v[2 * k].x));       // low half = first element
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w.y) : "f"(v[2 * k].w), "f"(v[2 * k].z));
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w.z) : "f"(v[2 * k + 1].y), "f"(v[2 * k + 1].x));
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w.w) : "f"(v[2 * k + 1].w), "f"(v[2 * k + 1].z));
                     dst[k] = w;
                 }
             }
@@ -360,8 +366,8 @@ int k1_pad_rows(int max_rows) { return round_up(max_rows > 0 ? max_rows : 1, K1_
 size_t k1_workspace_bytes(int P, int max_M, int max_N)
 {
     const size_t padM = (size_t)k1_pad_rows(max_M), padN = (size_t)k1_pad_rows(max_N);
-    // packed bests + half norms + (tensor-core path) bf16 copies of both descriptor sets (<= P * pad rows of 64 bytes each)
-    return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long) + (size_t)K1_D * 2) + 512;
+    // packed bests + half norms + (tensor-core path) f16 copies of both descriptor sets (<= P * pad rows of 64 bytes each) + range flags
+    return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long) + (size_t)K1_D * 2) + (size_t)P * 8 + 1024;
 }
 
 static int g_k1_algo = 1;                       // 0 = FP32 FFMA2 kernel, 1 = tensor-core filter + exact re-check (mutual_nn_tc.cu)
@@ -384,13 +390,16 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     float* hnb = reinterpret_cast<float*>(w); w += (size_t)P * padN * 4;
     w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
     uint4* src_bf = reinterpret_cast<uint4*>(w); w += (size_t)P * padM * K1_D * 2;          // total_M <= P * padM rows
-    uint4* tgt_bf = reinterpret_cast<uint4*>(w);
+    uint4* tgt_bf = reinterpret_cast<uint4*>(w); w += (size_t)P * padN * K1_D * 2;
+    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    int32_t* oor = reinterpret_cast<int32_t*>(w);                                           // [2][P]: source side, target side
     const bool tc = g_k1_algo == 1 && max_M > 0 && max_N > 0 && k1_tc_supported(D, total_M, total_N);
 
     {
         const long long na = (long long)P * padM, nb = (long long)P * padN;
-        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed, tc ? src_bf : nullptr);
-        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed, tc ? tgt_bf : nullptr);
+        if (tc) { cudaError_t e = cudaMemsetAsync(oor, 0, (size_t)P * 8, stream); if (e != cudaSuccess) return e; }
+        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed, tc ? src_bf : nullptr, oor);
+        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed, tc ? tgt_bf : nullptr, oor + P);
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -403,7 +412,7 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     if (g_k1_ev0) cudaEventRecord(g_k1_ev0, stream);
     if (max_M > 0 && max_N > 0) {
         if (tc) {
-            cudaError_t e = k1_tc_launch(src, tgt, src_bf, tgt_bf, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
+            cudaError_t e = k1_tc_launch(src, tgt, src_bf, tgt_bf, oor, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
             if (e != cudaSuccess) return e;
         } else {
             k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);

@@ -246,7 +246,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
              const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
              const float* __restrict__ hn_src, const float* __restrict__ hn_tgt, int pad_src, int pad_tgt,
              unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_packed,
-             int nblk_src, int splits_src, int splits_tgt)
+             const int32_t* __restrict__ out_of_range, int num_pairs, int nblk_src, int splits_src, int splits_tgt)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];      // no static shared memory in this kernel: base is 1024-aligned
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -272,6 +272,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
     const int os = off_str[p], N = off_str[p + 1] - os;
     const int row0 = bx * TC_BM;
     if (row0 >= M || N <= 0) return;
+    // a descriptor of this pair does not fit f16 (|x| > 65504 or non-finite): the filter's scores are meaningless (inf / NaN), so every row
+    // of the pair is scanned exactly by its warp.  The flags are only consumed after the main loop: their load latency costs nothing.
+    const int32_t oor_a = __ldg(out_of_range + p), oor_b = __ldg(out_of_range + num_pairs + p);
     const int ntiles_all = (N + TC_BN - 1) / TC_BN;
     const int t_begin = (int)(((long long)blockIdx.y * ntiles_all) / splits);
     const int t_end = (int)(((long long)(blockIdx.y + 1) * ntiles_all) / splits);
@@ -354,8 +357,8 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            // instruction descriptor (kind::f16): D = F32, A = B = BF16, both K-major, N = 256, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 256, M = 128
+            const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint64_t adesc0 = umma_desc_sw64(sm.a), adesc1 = umma_desc_sw64(sm.a + 128 * TC_D);
             mbar_wait(&sm.a_full, 0);
             for (int it = 0; it < ntiles; ++it) {
@@ -383,7 +386,10 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
         const int row = row0 + r;
         const bool valid = row < M;
         const float own_hn = valid ? hn_own[(size_t)p * pad_own + row] : 0.0f;
-        const float two_eps = 0.016f * sqrtf(fmaxf(-2.0f * own_hn, 0.0f) * fmaxf(str_max_sq, 0.0f)) + 1e-30f;      // 2 eps, eps = 1.024 * 2^-7 |a| max|b|
+        const float own_norm = sqrtf(fmaxf(-2.0f * own_hn, 0.0f)), str_norm = sqrtf(fmaxf(str_max_sq, 0.0f));
+        // 2 eps, eps = 1.0625 * 2^-10 |a| max|b| + 2^-22 (|a| + max|b|): f16 operands carry 11 significand bits (relative error 2^-11 each),
+        // or an absolute error of at most 2^-25 per element below the normal range
+        const float two_eps = 0.0020752f * own_norm * str_norm + 4.77e-7f * (own_norm + str_norm) + 1e-30f;
         // Streamed norms (nearly) uniform -- L2-normalised descriptors, BUFFER's case: rank full tiles on the raw dot products
         // (no hn add) and widen the band by the spread of hn; scores of hn-adjusted (partial) tiles are shifted by -hmax to match.
         const bool uniform = hn_spread <= 0.0009765625f * str_max_sq;   // CTA-uniform (the branch below contains warp-collective TMEM loads)
@@ -508,7 +514,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
         // columns of a group are fetched together (one memory round trip per group, usually one per row).
         {
             const float thr = m_run - band;
-            bool overflow = dropped_max >= thr;                       // a dropped event could still hold the maximum: exact scan of the row
+            bool overflow = (oor_a | oor_b) != 0 || !(dropped_max < thr);    // a dropped event could still hold the maximum (or thr is NaN): exact scan of the row
             const int j_end = min(N, t_end * TC_BN);
             const int sub = lane >> 3, chunk = lane & 7;
             // gather 32 rows (one per lane, row index `want`, -1 = none) of `base` into registers, 4 rows per instruction
@@ -667,14 +673,14 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int box
     cuuint64_t strides[1] = { (cuuint64_t)TC_D * 2 };
     cuuint32_t box[2] = { (cuuint32_t)TC_D, (cuuint32_t)box_rows };
     cuuint32_t estr[2] = { 1, 1 };
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool k1_tc_supported(int D, long long total_M, long long total_N) { return D == TC_D && total_M > 0 && total_N > 0 && encode_fn() != nullptr; }
 
 // both directions; hna/hnb/row_packed/col_packed are the (prepared, zeroed) workspace arrays of k1_launch
-cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_bf16, const void* tgt_bf16, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_bf16, const void* tgt_bf16, const int32_t* out_of_range, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
                          long long total_M, long long total_N, const float* hna, const float* hnb, int padM, int padN,
                          unsigned long long* row_packed, unsigned long long* col_packed, cudaStream_t stream)
 {
@@ -696,7 +702,7 @@ cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_bf1
     const int splits_tgt = (tiles_src + TC_MAX_TILES - 1) / TC_MAX_TILES > 0 ? (tiles_src + TC_MAX_TILES - 1) / TC_MAX_TILES : 1;   // tgt rows own, src streamed
     dim3 grid((unsigned)(nblk_src + nblk_tgt), (unsigned)(splits_src > splits_tgt ? splits_src : splits_tgt), (unsigned)P);
     k1_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(ms_own, mt_str, mt_own, ms_str, src, tgt, src_off, tgt_off, hna, hnb, padM, padN,
-                                                     row_packed, col_packed, nblk_src, splits_src, splits_tgt);
+                                                     row_packed, col_packed, out_of_range, P, nblk_src, splits_src, splits_tgt);
     return cudaGetLastError();
 }
 

@@ -73,6 +73,13 @@ def test_mutual_nn_adversarial_inputs(oracle, backend, algo):
     cases.append((z, nrm(torch.randn(450, 32, generator=g))))
     cases.append((1e3 * torch.randn(400, 32, generator=g), 1e3 * torch.randn(500, 32, generator=g)))
     cases.append((1e-3 * torch.randn(400, 32, generator=g), 1e-3 * torch.randn(500, 32, generator=g) * torch.rand(500, 1, generator=g)))
+    # beyond the f16 range of the tensor-core operands (|x| > 65504 -> the pair is scanned exactly), one side only, and far below it
+    cases.append((1e5 * torch.randn(300, 32, generator=g), 1e5 * torch.randn(350, 32, generator=g)))
+    cases.append((nrm(torch.randn(260, 32, generator=g)), 3e5 * torch.randn(300, 32, generator=g)))
+    cases.append((1e-6 * torch.randn(400, 32, generator=g), 1e-7 * torch.randn(500, 32, generator=g)))
+    cases.append((nrm(torch.randn(300, 32, generator=g)), 1e-6 * nrm(torch.randn(280, 32, generator=g))))
+    big = nrm(torch.randn(400, 32, generator=g)); big[7, 3] = 7e4                                     # a single out-of-range element
+    cases.append((big, nrm(torch.randn(380, 32, generator=g))))
     cases.append((nrm(torch.randn(300, 32, generator=g)), nrm(torch.randn(9000, 32, generator=g))))
     cases.append((nrm(torch.randn(9000, 32, generator=g)), nrm(torch.randn(300, 32, generator=g))))
     for src, tgt in cases:
@@ -412,7 +419,7 @@ def test_tensor_filter_equals_fp32_kernel_on_stress_inputs(backend):
             return nrm(c + 1e-3 * r(M, 32)), torch.cat([nrm(c + 1e-4 * r(N // 2, 32)), nrm(r(N - N // 2, 32))])
         src = r(M, 32) * 10.0 ** torch.empty(M, 1).uniform_(-2, 2, generator=g)          # "scaled"
         tgt = r(N, 32) * 10.0 ** torch.empty(N, 1).uniform_(-2, 2, generator=g)
-        tgt[::11] = tgt[1::11][: tgt[::11].shape[0]]; src[::13] = 0.0
+        nd = min(tgt[::11].shape[0], tgt[1::11].shape[0]); tgt[::11][:nd] = tgt[1::11][:nd]; src[::13] = 0.0
         return src, tgt
 
     cases = [("unrelated", 5000, 5000), ("clusters", 3100, 2900), ("flood", 1500, 2600), ("scaled", 2222, 3333), ("clusters", 700, 9000),

@@ -32,7 +32,7 @@ def make(g, M, N, kind):
     if kind == "scaled":                        # un-normalised, norms over four decades, some exact duplicates and zero rows
         src = r(M, 32) * 10.0 ** torch.empty(M, 1).uniform_(-2, 2, generator=g)
         tgt = r(N, 32) * 10.0 ** torch.empty(N, 1).uniform_(-2, 2, generator=g)
-        tgt[::11] = tgt[1::11][: tgt[::11].shape[0]]; src[::13] = 0.0
+        nd = min(tgt[::11].shape[0], tgt[1::11].shape[0]); tgt[::11][:nd] = tgt[1::11][:nd]; src[::13] = 0.0
         return src, tgt
     raise ValueError(kind)
 

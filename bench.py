@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config id (1-5); 2 is the one the metric is quoted on")
     ap.add_argument("--pairs", type=int, default=0, help="override the number of pairs per GPU (0 = the config's)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=0, help="pairs in the CPU baseline sample (0 = 4 per host thread)")
-    ap.add_argument("--k1-algo", type=int, default=1, help="0 = FP32 FFMA2 mutual-NN kernel, 1 = tcgen05 bf16 filter + exact FP32 re-check (bit-identical results)")
+    ap.add_argument("--k1-algo", type=int, default=1, help="0 = FP32 FFMA2 mutual-NN kernel, 1 = tcgen05 f16 filter + exact FP32 re-check (bit-identical results)")
     ap.add_argument("--e2e-chunk", type=int, default=64, help="pairs per host->device chunk of the e2e leg (two chunks in flight on two streams)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -325,15 +325,15 @@ def main():
                      "outputs_identical_to_tensor_path": k1_paths_identical}
         if args.k1_algo == 1:
             bf16_peak = mp.get("bf16_tflops") or 1590.0
-            # tensor-pipe floor of this formulation: one accumulator tile = 128 own rows x 256 streamed rows x K 32 = two back-to-back bf16 MMAs;
+            # tensor-pipe floor of this formulation: one accumulator tile = 128 own rows x 256 streamed rows x K 32 = two back-to-back f16 MMAs;
             # the pipe drains on every switch to another accumulator tile, ~345 cycles per tile whatever its N (profiles/r01_mma_pipeline_microbench.txt)
             tiles = 2.0 * P * ((N + 127) // 128) * ((N + 255) // 256)
             mma_floor_ms = tiles / 148.0 * 345.0 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)
-            roof = {"kernel": "k1_tc_kernel (one launch, both directions: tcgen05 bf16 filter, 128x256 accumulator tiles in TMEM + exact FP32 re-check)", "bound": "tensor",
+            roof = {"kernel": "k1_tc_kernel (one launch, both directions: tcgen05 f16 filter, 128x256 accumulator tiles in TMEM + exact FP32 re-check)", "bound": "tensor",
                     "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": traffic,
                     "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step, "algorithmic_flops_per_launch": flops_k1,
                     "executed_tensor_flops_per_launch": 2 * flops_k1,
-                    "peak_source": "dense bf16 = measured cuBLAS burst peak in MEASURED_PEAKS.json (%s)" % ("measured" if mp.get("bf16_tflops") else "fallback 1.59 PF"),
+                    "peak_source": "dense 16-bit tensor peak = measured cuBLAS bf16 burst in MEASURED_PEAKS.json (f16 and bf16 MMAs run at the same rate) (%s)" % ("measured" if mp.get("bf16_tflops") else "fallback 1.59 PF"),
                     "tensor_pipe_floor_ms": mma_floor_ms, "frac_of_tensor_pipe_floor": mma_floor_ms / k1_ms,
                     "note": "K = 32 gives two MMAs per accumulator tile, so the tensor pipe is bound by its ~345-cycle drain per tile (tensor_pipe_floor_ms), "
                             "not by FLOPs, and the kernel as a whole by the TMEM -> register max-reduction epilogue and the MMA <-> epilogue hand-off; "

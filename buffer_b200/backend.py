@@ -27,7 +27,7 @@ K1_FP32, K1_TENSOR_FILTER = 0, 1
 
 
 def set_k1_algo(algo):
-    """select the mutual-NN kernel: K1_FP32 (all products in FP32) or K1_TENSOR_FILTER (tcgen05 bf16 filter + exact FP32
+    """select the mutual-NN kernel: K1_FP32 (all products in FP32) or K1_TENSOR_FILTER (tcgen05 f16 filter + exact FP32
     re-check); outputs are bit-identical"""
     _lib.check(_lib.lib().bfr_config_set(1, int(algo)), "bfr_config_set")
 

@@ -389,8 +389,8 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     float* hna = reinterpret_cast<float*>(w); w += (size_t)P * padM * 4;
     float* hnb = reinterpret_cast<float*>(w); w += (size_t)P * padN * 4;
     w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
-    uint4* src_bf = reinterpret_cast<uint4*>(w); w += (size_t)P * padM * K1_D * 2;          // total_M <= P * padM rows
-    uint4* tgt_bf = reinterpret_cast<uint4*>(w); w += (size_t)P * padN * K1_D * 2;
+    uint4* src_h = reinterpret_cast<uint4*>(w); w += (size_t)P * padM * K1_D * 2;          // total_M <= P * padM rows
+    uint4* tgt_h = reinterpret_cast<uint4*>(w); w += (size_t)P * padN * K1_D * 2;
     w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
     int32_t* oor = reinterpret_cast<int32_t*>(w);                                           // [2][P]: source side, target side
     const bool tc = g_k1_algo == 1 && max_M > 0 && max_N > 0 && k1_tc_supported(D, total_M, total_N);
@@ -398,8 +398,8 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     {
         const long long na = (long long)P * padM, nb = (long long)P * padN;
         if (tc) { cudaError_t e = cudaMemsetAsync(oor, 0, (size_t)P * 8, stream); if (e != cudaSuccess) return e; }
-        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed, tc ? src_bf : nullptr, oor);
-        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed, tc ? tgt_bf : nullptr, oor + P);
+        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed, tc ? src_h : nullptr, oor);
+        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed, tc ? tgt_h : nullptr, oor + P);
     }
     static bool attr_set = false;
     if (!attr_set) {
@@ -412,7 +412,7 @@ cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off
     if (g_k1_ev0) cudaEventRecord(g_k1_ev0, stream);
     if (max_M > 0 && max_N > 0) {
         if (tc) {
-            cudaError_t e = k1_tc_launch(src, tgt, src_bf, tgt_bf, oor, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
+            cudaError_t e = k1_tc_launch(src, tgt, src_h, tgt_h, oor, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
             if (e != cudaSuccess) return e;
         } else {
             k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);

@@ -1,10 +1,13 @@
 // mutual_nn_tc.cu — K1-TC: tensor-core *filter* + exact FP32 re-check for the mutual-NN argmax (sm_100a, tcgen05/TMEM/TMA).
 //
 // Same contract and bit-exact results as k1_mutual_nn_kernel (mutual_nn.cu / oracle orc_mutual_nn), ~10x less FP32 work:
-//   1. S~ = A B^T with tcgen05.mma kind::f16 on bf16 copies of the descriptors (written by k1_prep_kernel; M = 128, N = 256,
-//      K = 16 per instruction, FP32 accumulators in TMEM).  bf16 keeps 8 significand bits, so |S~_ij - a_i.b_j| <=
-//      (2^-8 + 2^-16) |a_i||b_j|; with eps = 1.024 * 2^-7 |a_i| max_j|b_j| every column whose exact score could be the row maximum
-//      satisfies  S~_ij + hn(b_j) >= max_j(S~_ij + hn(b_j)) - 2 eps.
+//   1. S~ = A B^T with tcgen05.mma kind::f16 on f16 copies of the descriptors (written by k1_prep_kernel; M = 128, N = 256,
+//      K = 16 per instruction, FP32 accumulators in TMEM).  f16 keeps 11 significand bits (or an absolute error <= 2^-25 per element
+//      below its normal range), so |S~_ij - a_i.b_j| <= (2^-10 + 2^-22) |a_i||b_j| + 2^-25 sqrt(32) (|a_i| + |b_j|); with
+//      eps = 1.0625 * 2^-10 |a_i| max_j|b_j| + 2^-22 (|a_i| + max_j|b_j|) every column whose exact score could be the row maximum
+//      satisfies  S~_ij + hn(b_j) >= max_j(S~_ij + hn(b_j)) - 2 eps.  (bf16 operands, tried first, need a band 8x wider: 14 % slower on
+//      the benchmark workload, 29 % on descriptors without clear matches.)  A pair holding an element f16 cannot represent (|x| > 65504,
+//      non-finite) is flagged by the prep kernel; its rows skip the filter result and are scanned exactly.
 //   2. The epilogue (one thread per row, TMEM -> registers with tcgen05.ld) keeps the running approximate maximum and a short list of
 //      "events": 32-column chunks whose maximum was inside the 2-eps band when they streamed past, with their eight 4-column group
 //      maxima (compacted when the list runs low).
@@ -34,7 +37,7 @@ namespace bfr {
 constexpr int TC_BM = 256;                      // own rows per CTA = two M=128 accumulator halves sharing every streamed tile
 constexpr int TC_BN = 256;                      // streamed rows per tile = MMA N (the largest cta_group::1 shape: see the note on accumulator switches below)
 constexpr int TC_D = 32;
-constexpr int TC_MMAK = TC_D / 16;                // K = 16 per bf16 MMA
+constexpr int TC_MMAK = TC_D / 16;                // K = 16 per f16 MMA
 constexpr int TC_STAGES = 3;                     // streamed tiles in flight (3 x 16 KB)
 constexpr int TC_EPI_WARPS = 8;                 // one epilogue thread per own row
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
@@ -48,7 +51,7 @@ __device__ unsigned long long g_dbg[8];
 #endif
 
 struct TcSmem {
-    uint16_t a[TC_BM * TC_D];                   // 16 KB bf16, SWIZZLE_64B K-major (one 64-byte row per descriptor); rows 128.. = second half
+    uint16_t a[TC_BM * TC_D];                   // 16 KB f16, SWIZZLE_64B K-major (one 64-byte row per descriptor); rows 128.. = second half
     uint16_t b[TC_STAGES][TC_BN * TC_D];        // 3 x 16 KB (after the last MMA: uint32_t glist[TC_GCAP][TC_BM], the groups to re-check)
     float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
     struct Ev {                                 // band events of one epilogue warp (once consumed: the warp's 16 KB staging area of the re-check)
@@ -98,7 +101,7 @@ BFR_DEVINL uint64_t umma_desc_sw64(const void* smem)
 {   // K-major, SWIZZLE_64B: 8-row groups 512 B apart (SBO = 32 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell), layout 4 = SW64
     return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
-BFR_DEVINL void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+BFR_DEVINL void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
@@ -238,7 +241,7 @@ __device__ __noinline__ void warp_recheck_balanced(bool COLDIR, int n, int nmax,
 
 // One launch covers both directions of every pair: row blocks [0, nblk_src) of a pair own source rows and stream the target set
 // (-> row_packed), row blocks [nblk_src, gridDim.x) own target rows and stream the source set (-> col_packed).  The CTAs of a pair are
-// adjacent in launch order, so the second direction finds the pair's descriptors (FP32 and bf16) in L2.
+// adjacent in launch order, so the second direction finds the pair's descriptors (FP32 and f16) in L2.
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_constant__ CUtensorMap map_tgt_str,
              const __grid_constant__ CUtensorMap map_tgt_own, const __grid_constant__ CUtensorMap map_src_str,
@@ -335,7 +338,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
             mbar_expect_tx(&sm.a_full, TC_BM * TC_D * 2);
             tma_load_2d(sm.a, map_own, 0, oo + row0, &sm.a_full);
 #ifndef TC_NO_L2_PREFETCH
-            // The exact re-check reads FP32 rows the main loop never touches (it streams the bf16 copies): the CTA's own rows and a
+            // The exact re-check reads FP32 rows the main loop never touches (it streams the f16 copies): the CTA's own rows and a
             // scattered subset of the streamed set.  Pull them towards L2 now - the own rows, and this CTA's share of the streamed rows of
             // the pair (together the row blocks of a pair cover all of them) - so that the re-check waits for L2, not for DRAM.
             {
@@ -372,7 +375,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
                     const uint64_t ad = h ? adesc1 : adesc0;
 #pragma unroll
                     for (int k = 0; k < TC_MMAK; ++k)              // K = 16 per instruction: +32 bytes (2 x 16 B) per step inside the 64-byte row
-                        umma_bf16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
+                        umma_f16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
                     umma_commit(&sm.acc_full[h]);
                 }
                 umma_commit(&sm.empty[s]);                            // the stage is free once every MMA that reads it has completed
@@ -564,7 +567,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
 #pragma unroll
                 for (int c = 0; c < 8; ++c) rowv[c] = stage[buf * 256 + lane * 8 + (c ^ (lane & 7))];
             };
-            // own rows: staged once per warp in operand memory that is dead by now (the bf16 own tile / the third TMA stage), so that any
+            // own rows: staged once per warp in operand memory that is dead by now (the f16 own tile / the third TMA stage), so that any
             // lane can score any row of the warp in the balanced part and in the overflow scan
             float4* ownS = (ew < 4) ? reinterpret_cast<float4*>(sm.a) + ew * 256 : reinterpret_cast<float4*>(sm.b[2]) + (ew - 4) * 256;
             unsigned long long* bestS = reinterpret_cast<unsigned long long*>(stage + TC_SUB * 256);      // per-row maxima (packed)
@@ -680,13 +683,13 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int box
 bool k1_tc_supported(int D, long long total_M, long long total_N) { return D == TC_D && total_M > 0 && total_N > 0 && encode_fn() != nullptr; }
 
 // both directions; hna/hnb/row_packed/col_packed are the (prepared, zeroed) workspace arrays of k1_launch
-cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_bf16, const void* tgt_bf16, const int32_t* out_of_range, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_f16, const void* tgt_f16, const int32_t* out_of_range, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
                          long long total_M, long long total_N, const float* hna, const float* hnb, int padM, int padN,
                          unsigned long long* row_packed, unsigned long long* col_packed, cudaStream_t stream)
 {
     CUtensorMap ms_own, ms_str, mt_own, mt_str;
-    if (!make_map(&ms_own, src_bf16, total_M, TC_BM) || !make_map(&ms_str, src_bf16, total_M, TC_BN) ||
-        !make_map(&mt_own, tgt_bf16, total_N, TC_BM) || !make_map(&mt_str, tgt_bf16, total_N, TC_BN)) return cudaErrorNotSupported;
+    if (!make_map(&ms_own, src_f16, total_M, TC_BM) || !make_map(&ms_str, src_f16, total_M, TC_BN) ||
+        !make_map(&mt_own, tgt_f16, total_N, TC_BM) || !make_map(&mt_str, tgt_f16, total_N, TC_BN)) return cudaErrorNotSupported;
     const size_t smem = sizeof(TcSmem) + 1024;
     static bool once = false;
     if (!once) {

@@ -39,7 +39,7 @@ int bfr_version(void);
 const char* bfr_error_string(int code);
 
 /* Process-wide tuning knobs.  BFR_CFG_K1_ALGO selects the mutual-NN implementation: 0 = FP32 FFMA2 kernel (every product
- * in FP32), 1 = tensor-core (tcgen05, bf16 operands) filter followed by an exact FP32 re-check of the near-best candidates.  Both
+ * in FP32), 1 = tensor-core (tcgen05, f16 operands) filter followed by an exact FP32 re-check of the near-best candidates.  Both
  * produce bit-identical outputs. */
 #define BFR_CFG_K1_ALGO 1
 int bfr_config_set(int key, int value);

@@ -701,8 +701,18 @@ cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_f16
     // directions' counts; the other direction's surplus CTAs exit at once); z = pair
     const int nblk_src = (max_M + TC_BM - 1) / TC_BM, nblk_tgt = (max_N + TC_BM - 1) / TC_BM;
     const int tiles_tgt = (max_N + TC_BN - 1) / TC_BN, tiles_src = (max_M + TC_BN - 1) / TC_BN;
-    const int splits_src = (tiles_tgt + TC_MAX_TILES - 1) / TC_MAX_TILES > 0 ? (tiles_tgt + TC_MAX_TILES - 1) / TC_MAX_TILES : 1;   // src rows own, tgt streamed
-    const int splits_tgt = (tiles_src + TC_MAX_TILES - 1) / TC_MAX_TILES > 0 ? (tiles_src + TC_MAX_TILES - 1) / TC_MAX_TILES : 1;   // tgt rows own, src streamed
+    // column splits: as many as the hn cache demands (TC_MAX_TILES tiles per CTA); for small batches (the reference registers one pair per
+    // forward) more, so that the row blocks of one or two pairs still cover the 148 SMs in one wave (>= 4 tiles per CTA, at most 8 splits);
+    // rows merge across splits through the packed RED.MAX like across CTAs
+    const long long ctas = (long long)P * (nblk_src + nblk_tgt);
+    const int fill = ctas > 0 && ctas < 148 ? (int)(148 / ctas) : 1;
+    auto pick = [&](int tiles) {
+        int need = (tiles + TC_MAX_TILES - 1) / TC_MAX_TILES; if (need < 1) need = 1;
+        int want = fill; if (want > tiles / 4) want = tiles / 4; if (want > 8) want = 8;
+        return want > need ? want : need;
+    };
+    const int splits_src = pick(tiles_tgt);     // src rows own, tgt streamed
+    const int splits_tgt = pick(tiles_src);     // tgt rows own, src streamed
     dim3 grid((unsigned)(nblk_src + nblk_tgt), (unsigned)(splits_src > splits_tgt ? splits_src : splits_tgt), (unsigned)P);
     k1_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(ms_own, mt_str, mt_own, ms_str, src, tgt, src_off, tgt_off, hna, hnb, padM, padN,
                                                      row_packed, col_packed, out_of_range, P, nblk_src, splits_src, splits_tgt);

@@ -253,6 +253,21 @@ def main():
         r_tc = B.mutual_matching_batched(src_des, tgt_des, off, off, N, N, want_nn=True, want_mids=False)
         k1_paths_identical = bool(torch.equal(r_fp["nn_s"], r_tc["nn_s"]) and torch.equal(r_fp["nn_t"], r_tc["nn_t"]))
         del r_fp, r_tc
+        # ---- extra leg: the same K1 launch on UNRELATED descriptors (every pair matched against the next pair's targets: no true matches),
+        # the filter's worst realistic case (workload sensitivity) --------
+        k1_unrelated_ms = None
+        if P > 1:
+            tgt_roll = torch.roll(tgt_des.reshape(P, N, 32), 1, 0).reshape(P * N, 32).contiguous()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+            for a_, b_ in ev:
+                a_.record(); b_.record()
+            for a_, b_ in ev:
+                L.bfr_debug_set_k1_events(ctypes.c_void_p(a_.cuda_event), ctypes.c_void_p(b_.cuda_event))
+                B.mutual_matching_batched(src_des, tgt_roll, off, off, N, N, want_nn=True, want_mids=False)
+            L.bfr_debug_set_k1_events(None, None)
+            torch.cuda.synchronize()
+            k1_unrelated_ms = min(a_.elapsed_time(b_) for a_, b_ in ev)
+            del tgt_roll
         # ---- extra leg: K2+K3 alone on the same data (events on the launching stream), H_valid for the 28*H_valid*C work model --------
         rm = B.mutual_matching_batched(src_des, tgt_des, off, off, N, N, src_xyz, tgt_xyz, want_nn=False, want_mids=False)
         nvalid = torch.zeros(P, dtype=torch.int32, device=dev)
@@ -335,6 +350,7 @@ def main():
                     "executed_tensor_flops_per_launch": 2 * flops_k1,
                     "peak_source": "dense 16-bit tensor peak = measured cuBLAS bf16 burst in MEASURED_PEAKS.json (f16 and bf16 MMAs run at the same rate) (%s)" % ("measured" if mp.get("bf16_tflops") else "fallback 1.59 PF"),
                     "tensor_pipe_floor_ms": mma_floor_ms, "frac_of_tensor_pipe_floor": mma_floor_ms / k1_ms,
+                    "k1_ms_unrelated_descriptors": k1_unrelated_ms,
                     "note": "K = 32 gives two MMAs per accumulator tile, so the tensor pipe is bound by its ~345-cycle drain per tile (tensor_pipe_floor_ms), "
                             "not by FLOPs, and the kernel as a whole by the TMEM -> register max-reduction epilogue and the MMA <-> epilogue hand-off; "
                             "the algorithmic FLOP rate exceeds the FP32 roofline because the products run on tensor cores and only near-best candidates are re-evaluated in FP32",

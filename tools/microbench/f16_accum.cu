@@ -30,15 +30,17 @@ __device__ __forceinline__ void ld32(uint32_t taddr, uint32_t (&r)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 constexpr int N = 128;      // streamed rows (MMA N)
+constexpr int KMAX = 64;    // operand depth allocated (mode 3 uses all of it: 4 MMAs; the other modes use 32)
 // element (row, k) of a [rows x 32] bf16 operand in the no-swizzle K-major layout: core matrix = 8 rows x 8 elements (16 bytes per row)
 __device__ __forceinline__ int opnd_index(int row, int k, int rows) { return ((k >> 3) * (rows >> 3) + (row >> 3)) * 64 + (row & 7) * 8 + (k & 7); }
 
 __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* A, const __nv_bfloat16* B, float* out_f32, float* out_f16, uint32_t* raw_f16, int mode)
 {
-    __shared__ __align__(1024) __nv_bfloat16 sa[128 * 32], sb[N * 32];
+    __shared__ __align__(1024) __nv_bfloat16 sa[128 * KMAX], sb[N * KMAX];
+    const int KD = mode == 3 ? KMAX : 32;
     __shared__ uint32_t tb; __shared__ uint64_t bar;
-    for (int i = threadIdx.x; i < 128 * 32; i += 128) sa[opnd_index(i / 32, i % 32, 128)] = A[i];
-    for (int i = threadIdx.x; i < N * 32; i += 128) sb[opnd_index(i / 32, i % 32, N)] = B[i];
+    for (int i = threadIdx.x; i < 128 * KD; i += 128) sa[opnd_index(i / KD, i % KD, 128)] = A[i];
+    for (int i = threadIdx.x; i < N * KD; i += 128) sb[opnd_index(i / KD, i % KD, N)] = B[i];
     if (threadIdx.x == 0) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar))); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     if (threadIdx.x < 32) { asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tb)) : "memory");
                             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
@@ -47,12 +49,12 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* A, const __nv_
     const uint32_t lane_addr = tb + ((uint32_t)((threadIdx.x >> 5) * 32) << 16);
     uint32_t r[32];
     // mode 0: bf16 operands, F32 accumulator | mode 1: the operand bits are f16, F16 accumulator | mode 2: bf16 operands, F16 accumulator
-    for (int pass = (mode == 0 ? 0 : 1); pass < (mode == 0 ? 1 : 2); ++pass) {
+    for (int pass = ((mode == 0 || mode == 3) ? 0 : 1); pass < ((mode == 0 || mode == 3) ? 1 : 2); ++pass) {
         if (threadIdx.x == 0) {
             const uint32_t dfmt = pass == 0 ? 1u : 0u;
-            const uint32_t abfmt = mode == 1 ? 0u : 1u;              // 0 = F16, 1 = BF16
+            const uint32_t abfmt = (mode == 1 || mode == 3) ? 0u : 1u; // 0 = F16, 1 = BF16
             const uint32_t idesc = (dfmt << 4) | (abfmt << 7) | (abfmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            for (int ks = 0; ks < 2; ++ks) {                          // K = 16 per instruction = two core matrices along K
+            for (int ks = 0; ks < KD / 16; ++ks) {                    // K = 16 per instruction = two core matrices along K
                 const uint64_t ad = desc_noswz(sa + ks * 2 * (128 / 8) * 64, (128 / 8) * 128, 128);
                 const uint64_t bd = desc_noswz(sb + ks * 2 * (N / 8) * 64, (N / 8) * 128, 128);
                 mma(tb + (pass ? 256u : 0u), ad, bd, idesc, ks);
@@ -77,47 +79,54 @@ __global__ void __launch_bounds__(128) probe(const __nv_bfloat16* A, const __nv_
 int main(int argc, char** argv)
 {
     const int mode = argc > 1 ? atoi(argv[1]) : 0;
-    const int M = 128;
-    uint16_t *hA = new uint16_t[M * 32], *hB = new uint16_t[N * 32];
-    float *fA = new float[M * 32], *fB = new float[N * 32];
+    const int M = 128, KD = mode == 3 ? KMAX : 32;
+    uint16_t *hA = new uint16_t[M * KD], *hB = new uint16_t[N * KD];
+    float *fA = new float[M * KD], *fB = new float[N * KD];
     srand(7);
     auto fill = [&](uint16_t* h, float* f, int rows) {
         for (int i = 0; i < rows; ++i) {
-            float v[32], nn = 0; for (int k = 0; k < 32; ++k) { v[k] = (rand() / (float)RAND_MAX) * 2 - 1; nn += v[k] * v[k]; }
-            for (int k = 0; k < 32; ++k) {
-                const float x = v[k] / sqrtf(nn);
-                if (mode == 1) { __half hx = __float2half(x); memcpy(&h[i * 32 + k], &hx, 2); f[i * 32 + k] = __half2float(hx); }
-                else { __nv_bfloat16 bx = __float2bfloat16(x); memcpy(&h[i * 32 + k], &bx, 2); f[i * 32 + k] = __bfloat162float(bx); }
+            float v[KMAX], nn = 0; for (int k = 0; k < KD; ++k) { v[k] = (rand() / (float)RAND_MAX) * 2 - 1; nn += v[k] * v[k]; }
+            for (int k = 0; k < KD; ++k) {
+                const float x = mode == 3 ? 8.0f * v[k] : v[k] / sqrtf(nn);          // mode 3: magnitudes up to 8, products up to 64, heavy cancellation
+                if (mode == 1 || mode == 3) { __half hx = __float2half(x); memcpy(&h[i * KD + k], &hx, 2); f[i * KD + k] = __half2float(hx); }
+                else { __nv_bfloat16 bx = __float2bfloat16(x); memcpy(&h[i * KD + k], &bx, 2); f[i * KD + k] = __bfloat162float(bx); }
             }
         }
     };
     fill(hA, fA, M); fill(hB, fB, N);
     __nv_bfloat16 *dA, *dB; float *d32, *d16; uint32_t* draw;
-    cudaMalloc(&dA, M * 32 * 2); cudaMalloc(&dB, N * 32 * 2); cudaMalloc(&d32, M * N * 4); cudaMalloc(&d16, M * N * 4); cudaMalloc(&draw, M * N * 4);
-    cudaMemcpy(dA, hA, M * 32 * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, N * 32 * 2, cudaMemcpyHostToDevice);
+    cudaMalloc(&dA, M * KD * 2); cudaMalloc(&dB, N * KD * 2); cudaMalloc(&d32, M * N * 4); cudaMalloc(&d16, M * N * 4); cudaMalloc(&draw, M * N * 4);
+    cudaMemcpy(dA, hA, M * KD * 2, cudaMemcpyHostToDevice); cudaMemcpy(dB, hB, N * KD * 2, cudaMemcpyHostToDevice);
     cudaMemset(draw, 0, M * N * 4); cudaMemset(d32, 0, M * N * 4);
+    cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 0);
     probe<<<1, 128>>>(dA, dB, d32, d16, draw, mode);
     cudaError_t e = cudaDeviceSynchronize();
-    printf("mode %d (%s): kernel: %s\n", mode, mode == 0 ? "bf16 operands, F32 accumulator" : mode == 1 ? "f16 operands, F16 accumulator" : "bf16 operands, F16 accumulator", cudaGetErrorString(e));
+    const char* names[] = { "bf16 operands, F32 accumulator", "f16 operands, F16 accumulator", "bf16 operands, F16 accumulator", "f16 operands up to 8, K = 64, F32 accumulator" };
+    printf("mode %d (%s): kernel: %s\n", mode, names[mode], cudaGetErrorString(e));
     if (e != cudaSuccess) return 0;
     float* o32 = new float[M * N]; uint32_t* raw = new uint32_t[M * N];
     cudaMemcpy(o32, d32, M * N * 4, cudaMemcpyDeviceToHost); cudaMemcpy(raw, draw, M * N * 4, cudaMemcpyDeviceToHost);
-    double e32 = 0, e16_lo = 0, e16_packed = 0;
+    double e32 = 0, e16_lo = 0, e16_packed = 0, rel_abs = 0, rel_seq = 0;
     for (int i = 0; i < M; ++i)
         for (int j = 0; j < N; ++j) {
-            double s = 0; for (int k = 0; k < 32; ++k) s += (double)fA[i * 32 + k] * fB[j * 32 + k];
+            double s = 0, sabs = 0; float seq = 0.0f;
+            for (int k = 0; k < KD; ++k) { const double pr = (double)fA[i * KD + k] * fB[j * KD + k]; s += pr; sabs += fabs(pr); seq = fmaf(fA[i * KD + k], fB[j * KD + k], seq); }
             e32 = fmax(e32, fabs(o32[i * N + j] - s));
+            rel_abs = fmax(rel_abs, fabs(o32[i * N + j] - s) / sabs);
+            rel_seq = fmax(rel_seq, fabs((double)seq - s) / sabs);
             __half lo; uint16_t b = (uint16_t)(raw[i * N + j] & 0xFFFF); memcpy(&lo, &b, 2);
             e16_lo = fmax(e16_lo, fabs(__half2float(lo) - s));
             uint32_t w = raw[i * N + j / 2]; uint16_t hb = (uint16_t)((j & 1) ? (w >> 16) : (w & 0xFFFF)); __half hv; memcpy(&hv, &hb, 2);
             e16_packed = fmax(e16_packed, fabs(__half2float(hv) - s));
         }
     if (mode == 0) printf("F32 accumulator: max |D - exact| = %.3e (operand layout check: must be ~1e-7)\n", e32);
+    else if (mode == 3) printf("F32 accumulator over %d products: max |D - exact| = %.3e; relative to sum|a_k b_k|: %.3e = 2^%.1f (a sequential FP32 fma chain on the same data: 2^%.1f)\n",
+                               KD, e32, rel_abs, log2(rel_abs), log2(rel_seq));
     else {
         printf("F16 accumulator, one value per column (low half):   max |D - exact| = %.3e\n", e16_lo);
         printf("F16 accumulator, two values packed per column:      max |D - exact| = %.3e\n", e16_packed);
         printf("raw row 0, columns 0..3: %08x %08x %08x %08x   columns %d..%d: %08x %08x\n", raw[0], raw[1], raw[2], raw[3], N / 2, N / 2 + 1, raw[N / 2], raw[N / 2 + 1]);
-        printf("(2^-11 = 4.9e-4 is the F16 rounding step near 1; 2^-8 |a||b| = 3.9e-3 is the bf16 operand bound the filter budgets for)\n");
+        printf("(2^-11 = 4.9e-4 is the F16 rounding step near 1; 2^-8 |a||b| = 3.9e-3 is the bf16 operand bound)\n");
     }
     return 0;
 }

@@ -66,7 +66,7 @@ int bfr_mutual_matching_batched(const float* src_des, const float* tgt_des, cons
 {
     if (P == 0) return BFR_OK;
     if (!src_des || !tgt_des || !src_off || !tgt_off || !ws) return BFR_E_NULL;
-    if (P < 0 || max_M < 0 || max_N < 0 || total_M < 0 || total_N < 0) return BFR_E_SIZE;
+    if (P < 0 || P > BFR_MAX_PAIRS || max_M < 0 || max_N < 0 || total_M < 0 || total_N < 0) return BFR_E_SIZE;
     if (D != 32) return BFR_E_DIM;
     if (!aligned16(src_des) || !aligned16(tgt_des)) return BFR_E_ALIGN;
     if (ws_bytes < k1_workspace_bytes(P, max_M, max_N)) return BFR_E_WORKSPACE;
@@ -90,7 +90,7 @@ int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int
 {
     if (P == 0) return BFR_OK;
     if (!corr_xyz || !corr_off || !corr_cnt || !best_packed) return BFR_E_NULL;
-    if (P < 0 || h_end < h_begin) return BFR_E_SIZE;
+    if (P < 0 || P > BFR_MAX_PAIRS || h_end < h_begin) return BFR_E_SIZE;
     if (!aligned16(corr_xyz)) return BFR_E_ALIGN;
     return cu(ransac_launch(corr_xyz, corr_off, corr_cnt, P, seed, pair_id_base, h_begin, h_end, dist_th, similar_th, splits,
                             reinterpret_cast<unsigned long long*>(best_packed), valid_count, st(stream)));
@@ -163,7 +163,7 @@ int bfr_register_batched(const float* src_des, const float* src_xyz, const int32
     (void)total_N;
     if (P == 0) return BFR_OK;
     if (!src_des || !src_xyz || !src_off || !tgt_des || !tgt_xyz || !tgt_off || !T_out || !n_mutual || !ws) return BFR_E_NULL;
-    if (P < 0 || max_M < 0 || max_N < 0 || total_M < 0 || hypotheses < 0 || refine_iters < 0) return BFR_E_SIZE;
+    if (P < 0 || P > BFR_MAX_PAIRS || max_M < 0 || max_N < 0 || total_M < 0 || hypotheses < 0 || refine_iters < 0) return BFR_E_SIZE;
     if (D != 32) return BFR_E_DIM;
     if (!aligned16(src_des) || !aligned16(tgt_des)) return BFR_E_ALIGN;
     if (ws_bytes < reg_ws_bytes(P, max_M, max_N, total_M)) return BFR_E_WORKSPACE;
@@ -198,7 +198,7 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
 {
     if (P == 0) return BFR_OK;
     if (!src_des_host || !src_xyz_host || !tgt_des_host || !tgt_xyz_host || !T_out_host || !ws) return BFR_E_NULL;
-    if (P < 0 || M < 0 || N < 0) return BFR_E_SIZE;
+    if (P < 0 || P > BFR_MAX_PAIRS || M < 0 || N < 0) return BFR_E_SIZE;
     if (D != 32) return BFR_E_DIM;
     if (ws_bytes < bfr_register_host_workspace_bytes(P, M, N, D)) return BFR_E_WORKSPACE;
     cudaStream_t s = st(stream);

@@ -30,7 +30,8 @@ extern "C" {
 
 #define BFR_OK 0
 #define BFR_E_NULL (-1)      /* required pointer is NULL */
-#define BFR_E_SIZE (-2)      /* negative / inconsistent size */
+#define BFR_E_SIZE (-2)      /* negative / inconsistent size, or more than BFR_MAX_PAIRS pairs in one call */
+#define BFR_MAX_PAIRS 65535   /* pairs per batched call (one grid dimension); larger batches are split by the caller */
 #define BFR_E_DIM (-3)       /* unsupported descriptor length (this build: D == 32) */
 #define BFR_E_WORKSPACE (-4) /* workspace too small */
 #define BFR_E_ALIGN (-5)     /* pointer not 16-byte aligned */

@@ -70,6 +70,11 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.bfr_mutual_matching_batched(None, None, None, None, 1, 1, 1, 1, 1, 32, 1, None, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
     assert L.bfr_ransac_batched(None, None, None, 0, 0, 0, 0, 0, 0.1, 0.8, 1, None, None, None) == 0     # P == 0 is a no-op
     assert L.bfr_rigid_transform_3d(None, None, None, 3, 3, 0.0, None, None) == -1
+    # more than BFR_MAX_PAIRS pairs in one call is an argument error (BFR_E_SIZE), reported before anything touches the device
+    buf = ctypes.create_string_buffer(64)
+    ptr = ctypes.cast(buf, ctypes.c_void_p)
+    assert L.bfr_mutual_matching_batched(ptr, ptr, ptr, ptr, 70000, 1, 1, 1, 1, 32, 1, None, None, None, None, None, None, None, None, None, None, ptr, 1 << 40, None) == -2
+    assert L.bfr_ransac_batched(ptr, ptr, ptr, 70000, 0, 0, 0, 10, 0.1, 0.8, 1, ptr, None, None) == -2
 
 
 def test_product_never_imports_oracle():

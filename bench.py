@@ -180,6 +180,8 @@ def main():
         return
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    if world > 1:
+        bind_to_gpu_cpus(local)              # pinned host buffers of the e2e leg are then first-touched on the GPU's own NUMA node
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -386,6 +388,24 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bind_to_gpu_cpus(index):
+    """multi-GPU runs: restrict this rank to the CPUs NVML reports as local to its GPU (what `numactl --cpunodebind` would do), so that
+    the pinned host memory of the end-to-end leg is allocated next to the PCIe root the GPU hangs off; silently skipped without NVML"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 def _measured_peaks():

@@ -18,18 +18,24 @@ SIGNATURES = {
     "bfr_config_get": (_i, [_i]),
     "bfr_mutual_nn_workspace_bytes": (_sz, [_i, _i, _i]),
     "bfr_mutual_matching_batched": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bfr_mutual_nn_partial": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "bfr_mutual_nn_packed": (_i, [_vp, _sz, _i, _i, _i, _vp, _vp]),
+    "bfr_mutual_select": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_gather_corr": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
-    "bfr_ransac_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _u32, _u32, _f, _f, _i, _vp, _vp, _vp]),
+    "bfr_ransac_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _u32, _u32, _f, _f, _f, _i, _vp, _vp, _vp]),
     "bfr_ransac_finalize_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "bfr_lrf_hypotheses": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "bfr_score_workspace_bytes": (_sz, [_i]),
     "bfr_score_hypotheses": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bfr_vote_workspace_bytes": (_sz, [_i, _i]),
+    "bfr_lrf_vote_batched": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bfr_pose_from_votes_batched": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _f, _f, _i, _u64, _u32, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_rigid_transform_3d": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp]),
-    "bfr_post_refinement_batched": (_i, [_vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp, _vp, _vp]),
+    "bfr_post_refinement_batched": (_i, [_vp, _vp, _vp, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp]),
     "bfr_register_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "bfr_register_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u64, _u32, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bfr_register_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u64, _u32, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_register_host_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "bfr_register_uniform_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u64, _u32, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bfr_register_uniform_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u64, _u32, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_get_matching_indices_workspace_bytes": (_sz, [_i]),
     "bfr_get_matching_indices": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_svd3_batched": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),

@@ -36,8 +36,27 @@ def get_k1_algo():
     return _lib.lib().bfr_config_get(1)
 
 
-def _stream():
-    return torch.cuda.current_stream().cuda_stream
+def _stream(device=None):
+    """raw handle of torch's current stream on `device` (default: the current device)"""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _guard(fn):
+    """The library launches on the CURRENT device of the calling thread (include/buffer_b200.h): make the device that owns the
+    first CUDA tensor argument current for the duration of the call, so tensors on a non-current GPU work and `_stream()` is that
+    device's current stream."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        for a in list(args) + list(kw.values()):
+            if torch.is_tensor(a) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kw)
+                break
+        return fn(*args, **kw)
+    return wrapped
 
 
 def _ptr(t):
@@ -46,7 +65,7 @@ def _ptr(t):
 
 def _ws(nbytes, device, tag="default"):
     """grow-only scratch buffer per (device, stream, tag); caller-owned memory for the C ABI"""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(), tag)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream(device), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
@@ -71,11 +90,13 @@ def _offsets(counts, device):
 # ---------------------------------------------------------------------------------------------------------------
 # K1
 # ---------------------------------------------------------------------------------------------------------------
+@_guard
 def mutual_matching_batched(src_des, tgt_des, src_off, tgt_off, max_M, max_N, src_xyz=None, tgt_xyz=None,
                             want_nn=True, want_dist=False, want_mids=True, col_splits=None):
     """Batched varlen mutual matching, all on device, no sync.
 
-    src_des [totM, 32], tgt_des [totN, 32] float32; src_off/tgt_off int32 device [P+1].
+    src_des [totM, 32], tgt_des [totN, 32] float32; src_off/tgt_off int32 device [P+1].  max_M / max_N must be >= every
+    pair's row count (a larger pair is truncated to the bound by the kernels, never read out of its workspace slice).
     Returns dict: nn_s [totM] / nn_t [totN] int64 (pair-local), s_mids/t_mids [totM] int64 (pair p's matches at
     src_off[p] .. src_off[p]+n_mutual[p]), n_mutual [P] int32, corr [totM, 8] float32 (if keypoints given),
     dist_s/dist_t (if want_dist).
@@ -115,6 +136,7 @@ def mutual_matching_batched(src_des, tgt_des, src_off, tgt_off, max_M, max_N, sr
     return out
 
 
+@_guard
 def mutual_matching_device(src_des, tgt_des, src_xyz=None, tgt_xyz=None, want_dist=False):
     """single pair, device tensors in / out, no sync (s_mids/t_mids padded to M; valid prefix = n_mutual[0])"""
     dev = src_des.device
@@ -142,6 +164,7 @@ def knn1(ref, query):
 # ---------------------------------------------------------------------------------------------------------------
 # K2 + K3
 # ---------------------------------------------------------------------------------------------------------------
+@_guard
 def gather_corr(src_xyz, tgt_xyz, s_ids, t_ids):
     """(pcd0, pcd1, corr) of the Open3D call (models/BUFFER.py:314-316) -> correspondence records [K, 8]"""
     src_xyz = _f32c(src_xyz, "src_xyz"); tgt_xyz = _f32c(tgt_xyz, "tgt_xyz")
@@ -153,23 +176,27 @@ def gather_corr(src_xyz, tgt_xyz, s_ids, t_ids):
     return corr[:K] if K else corr[:0]
 
 
+@_guard
 def ransac_batched(corr, corr_off, corr_cnt, hypotheses, dist_th, similar_th, seed=0, pair_id_base=0, h_begin=0, h_end=None,
-                   splits=None, best_packed=None, valid_count=None):
+                   splits=None, best_packed=None, valid_count=None, confidence=1.0):
     """Evaluate hypotheses [h_begin, h_end) of every pair; max-accumulate into best_packed [P] (int64 view of the
-    packed uint64 (count << 32) | (0xFFFFFFFF - h)).  Device only, no sync."""
+    packed uint64 (count << 32) | (0xFFFFFFFF - h)).  Device only, no sync.  confidence in (0, 1): Open3D's
+    RANSACConvergenceCriteria early exit, replayed exactly as one sequential thread would run it (models/BUFFER.py:323-324);
+    the call must then cover the pair's whole hypothesis range."""
     corr = _f32c(corr, "corr")
     P = corr_cnt.numel()
     h_end = hypotheses if h_end is None else h_end
     if best_packed is None:
         best_packed = torch.zeros(P, dtype=torch.int64, device=corr.device)
     if splits is None:
-        splits = max(1, min(64, (296 + P - 1) // max(P, 1)))
+        splits = _default_splits(P)
     _lib.check(_lib.lib().bfr_ransac_batched(corr.data_ptr(), corr_off.data_ptr(), corr_cnt.data_ptr(), P, int(seed), int(pair_id_base),
-                                             int(h_begin), int(h_end), float(dist_th), float(similar_th), int(splits),
+                                             int(h_begin), int(h_end), float(dist_th), float(similar_th), float(confidence), int(splits),
                                              best_packed.data_ptr(), _ptr(valid_count), _stream()), "bfr_ransac_batched")
     return best_packed
 
 
+@_guard
 def ransac_finalize_batched(corr, corr_off, corr_cnt, best_packed, dist_th, similar_th, seed=0, pair_id_base=0):
     """-> T [P,4,4] float32, inliers [P] int32, best_h [P] int64 (device)"""
     P = corr_cnt.numel(); dev = corr.device
@@ -182,6 +209,11 @@ def ransac_finalize_batched(corr, corr_off, corr_cnt, best_packed, dist_th, simi
     return T, inl, bh
 
 
+def _default_splits(P):
+    """work items per pair of the persistent RANSAC kernel (one 512-thread CTA per SM): enough items to balance 148 SMs"""
+    return max(1, min(64, (4 * 148 + P - 1) // max(P, 1)))
+
+
 class RansacResult:
     """mimics the fields of open3d.pipelines.registration.RegistrationResult the reference reads (models/BUFFER.py:326)"""
 
@@ -192,20 +224,22 @@ class RansacResult:
         self.best_hypothesis = best_hypothesis
 
 
+@_guard
 def registration_ransac_based_on_correspondence(src_kpts, tgt_kpts, corr, max_correspondence_distance, similar_th,
                                                 iter_n=50000, confidence=1.0, seed=0, pair_id=0):
     """Drop-in for the Open3D call at models/BUFFER.py:318-324 with the checkers the reference passes.
 
     src_kpts [A,3], tgt_kpts [A,3] CUDA tensors, corr [K,2] integer tensor/array.  Returns an object whose
     ``.transformation`` is a 4x4 float64 numpy array (minimal-sample fit of the best hypothesis; identity if K < 3 or
-    nothing valid).  All `iter_n` hypotheses are evaluated (no confidence early-exit; `confidence` is accepted for
-    signature compatibility), best = max inlier count, ties -> lowest hypothesis index."""
+    nothing valid).  `confidence` = RANSACConvergenceCriteria's second argument: 1.0 (KITTI/config.py:65) evaluates all
+    `iter_n` hypotheses, a value in (0, 1) (ThreeDMatch/config.py:65 = 0.999) stops like Open3D's sequential loop does.
+    best = max inlier count, ties -> lowest hypothesis index."""
     dev = src_kpts.device
     corr = torch.as_tensor(np.asarray(corr) if not torch.is_tensor(corr) else corr).to(dev).to(torch.int64).reshape(-1, 2)
     K = corr.shape[0]
     rec = gather_corr(src_kpts, tgt_kpts, corr[:, 0], corr[:, 1]) if K else torch.zeros(1, 8, device=dev)
     off = torch.tensor([0, K], dtype=torch.int32).to(dev); cnt = torch.tensor([K], dtype=torch.int32).to(dev)
-    best = ransac_batched(rec, off, cnt, iter_n, max_correspondence_distance, similar_th, seed, pair_id)
+    best = ransac_batched(rec, off, cnt, iter_n, max_correspondence_distance, similar_th, seed, pair_id, confidence=confidence)
     T, inl, bh = ransac_finalize_batched(rec, off, cnt, best, max_correspondence_distance, similar_th, seed, pair_id)
     n = int(inl.item())
     return RansacResult(T[0].double().cpu().numpy(), n / max(K, 1), n, int(bh.item()))
@@ -222,6 +256,7 @@ def lrf_hypotheses(ind, ss_R, tt_R, ss_kpts, tt_kpts, azi_n=20):
     return lrf_hypotheses_cs(cs, ss_R, tt_R, ss_kpts, tt_kpts)
 
 
+@_guard
 def lrf_hypotheses_cs(cs, ss_R, tt_R, ss_kpts, tt_kpts):
     cs = _f32c(cs, "cs"); ss_R = _f32c(ss_R, "ss_R"); tt_R = _f32c(tt_R, "tt_R")
     ss_kpts = _f32c(ss_kpts, "ss_kpts"); tt_kpts = _f32c(tt_kpts, "tt_kpts")
@@ -232,6 +267,7 @@ def lrf_hypotheses_cs(cs, ss_R, tt_R, ss_kpts, tt_kpts):
     return R, t
 
 
+@_guard
 def score_hypotheses(R, t, src, tgt, thr):
     """models/BUFFER.py:303-311 -> (inlier_num [H] int32, best_ind [1] int64, inlier_mask [C] bool), device, no sync.
     thr: python float or [C] tensor."""
@@ -257,6 +293,7 @@ def inlier_threshold(ss_kpts, azi_n=20, inlier_th=1 / 3):
 # ---------------------------------------------------------------------------------------------------------------
 # K4
 # ---------------------------------------------------------------------------------------------------------------
+@_guard
 def rigid_transform_3d(A, B, weights=None, weight_threshold=0):
     """Drop-in for rigid_transform_3d (models/BUFFER.py:424-464): A, B [bs,n,3], weights [bs,n] -> [bs,4,4] on
     A's device.  Like the reference it zeroes weights below the threshold IN PLACE (:437)."""
@@ -277,18 +314,23 @@ def refine_threshold(dataset):
     return 0.10 if dataset in ("3DMatch", "3DLoMatch", "ETH") else 1.2
 
 
-def post_refinement_batched(T0, corr, corr_off, corr_cnt, thr, max_iter=20):
-    """-> T [P,4,4], iters [P], inliers [P] (device, no sync)"""
+@_guard
+def post_refinement_batched(T0, corr, corr_off, corr_cnt, thr, max_iter=20, max_count=None):
+    """-> T [P,4,4], iters [P], inliers [P] (device, no sync).  max_count: host-side upper bound of corr_cnt (default: the rows
+    of `corr`); above 16384 every pair is refined by an 8-CTA cluster (same reduction tree, same bits)."""
+    if max_count is None:
+        max_count = corr.shape[0]
     T0 = _f32c(T0, "T0").reshape(-1, 16); corr = _f32c(corr, "corr")
     P = corr_cnt.numel(); dev = corr.device
     T = torch.empty(P, 4, 4, dtype=torch.float32, device=dev)
     it = torch.empty(P, dtype=torch.int32, device=dev); inl = torch.empty(P, dtype=torch.int32, device=dev)
     _lib.check(_lib.lib().bfr_post_refinement_batched(T0.data_ptr(), corr.data_ptr(), corr_off.data_ptr(), corr_cnt.data_ptr(), P, float(thr),
-                                                      int(max_iter), T.data_ptr(), it.data_ptr(), inl.data_ptr(), _stream()),
+                                                      int(max_iter), int(max_count), T.data_ptr(), it.data_ptr(), inl.data_ptr(), _stream()),
                "bfr_post_refinement_batched")
     return T, it, inl
 
 
+@_guard
 def post_refinement(initial_trans, src_keypts, tgt_keypts, weights=None, dataset="3DMatch"):
     """Drop-in for buffer.post_refinement (models/BUFFER.py:382-418): [1,4,4], [1,n,3], [1,n,3] -> [1,4,4].
     `weights` is ignored exactly as in the reference; the whole <=20-round loop runs in one kernel, no host sync."""
@@ -305,6 +347,7 @@ def post_refinement(initial_trans, src_keypts, tgt_keypts, weights=None, dataset
 # ---------------------------------------------------------------------------------------------------------------
 # "next" rows
 # ---------------------------------------------------------------------------------------------------------------
+@_guard
 def get_matching_indices_device(source, target, relt_pose, search_voxel_size):
     """no-sync variant -> (match_inds [N,2] int64 padded, count [1] int32, nn [N] int64, dist [N] float32)"""
     source = _f32c(source, "source"); target = _f32c(target, "target"); T = _f32c(relt_pose, "relt_pose").reshape(16)
@@ -325,6 +368,7 @@ def get_matching_indices(source, target, relt_pose, search_voxel_size):
     return pairs[: int(count.item())]
 
 
+@_guard
 def svd(x):
     """torch_batch_svd.svd drop-in (utils/common.py:10,715): x [B,3,3] CUDA -> (u [B,3,3], s [B,3] descending, v [B,3,3])"""
     x = _f32c(x, "x")
@@ -336,6 +380,7 @@ def svd(x):
     return u, s, v
 
 
+@_guard
 def furthest_point_sample(xyz, npoint):
     """pointnet2_ops.furthest_point_sample drop-in (models/BUFFER.py:266-267): xyz [B,N,3] CUDA -> idx [B,npoint] int32"""
     xyz = _f32c(xyz, "xyz")
@@ -351,21 +396,135 @@ def gather_operation(features, idx):
     return torch.gather(features, 2, idx.long()[:, None, :].expand(-1, features.shape[1], -1))
 
 
+def _records(ss_kpts, tt_kpts):
+    """[A,3] + [A,3] -> correspondence records [A,8] (sx sy sz 0 | qx qy qz 0)"""
+    A = ss_kpts.shape[0]
+    rec = torch.zeros(max(A, 1), 8, dtype=torch.float32, device=ss_kpts.device)
+    rec[:A, 0:3] = ss_kpts; rec[:A, 4:7] = tt_kpts
+    return rec
+
+
+@_guard
+def lrf_vote_batched(corr, corr_off, corr_cnt, ind, ss_R, tt_R, max_count, azi_n=20, inlier_th=1 / 3, want_counts=True, want_ind=True):
+    """The LRF vote (models/BUFFER.py:294-311) for P pairs in one call, everything on the device, no sync: R and t only exist in
+    registers.  corr [rows,8] = records of ALL mutual matches (K1's `corr`; the 4th float of each record is overwritten with the
+    vote threshold), ind [rows] float32, ss_R / tt_R [rows,3,3], row-aligned with corr.
+    -> dict: inlier_num [rows] int32, best_ind [P] int64, sub_corr [rows,8] (each pair's voted subset at its offset: RANSAC's
+    input), sub_cnt [P] int32, inlier_ind [rows] int64 (pair-local indices of the subset, ascending)."""
+    corr = _f32c(corr, "corr"); ind = _f32c(ind, "ind"); ss_R = _f32c(ss_R, "ss_R"); tt_R = _f32c(tt_R, "tt_R")
+    dev = corr.device
+    rows, P = corr.shape[0], corr_cnt.numel()
+    out = {"inlier_num": torch.zeros(rows, dtype=torch.int32, device=dev) if want_counts else None,
+           "best_ind": torch.empty(P, dtype=torch.int64, device=dev),
+           "sub_corr": torch.empty(max(rows, 1), 8, dtype=torch.float32, device=dev),
+           "sub_cnt": torch.empty(P, dtype=torch.int32, device=dev),
+           "inlier_ind": torch.empty(max(rows, 1), dtype=torch.int64, device=dev) if want_ind else None}
+    L = _lib.lib()
+    ws = _ws(L.bfr_vote_workspace_bytes(P, 0), dev, "vote")
+    _lib.check(L.bfr_lrf_vote_batched(corr.data_ptr(), corr_off.data_ptr(), corr_cnt.data_ptr(), P, int(max_count), rows, ind.data_ptr(), ss_R.data_ptr(),
+                                      tt_R.data_ptr(), float(azi_n), float(inlier_th), _ptr(out["inlier_num"]), out["best_ind"].data_ptr(),
+                                      out["sub_corr"].data_ptr(), out["sub_cnt"].data_ptr(), _ptr(out["inlier_ind"]), ws.data_ptr(), ws.numel(), _stream()),
+               "bfr_lrf_vote_batched")
+    return out
+
+
 def lrf_vote(ind, ss_R, tt_R, ss_kpts, tt_kpts, azi_n=20, inlier_th=1 / 3):
-    """lines 294-311 of models/BUFFER.py in one call, everything stays on the device (no .cpu() at :311):
-    -> R [A,3,3], t [A,3], inlier_num [A] int32, best_ind [1] int64, inlier_mask [A] bool"""
-    R, t = lrf_hypotheses(ind, ss_R, tt_R, ss_kpts, tt_kpts, azi_n)
-    counts, best, mask = score_hypotheses(R, t, ss_kpts, tt_kpts, inlier_threshold(_f32c(ss_kpts, "ss_kpts"), azi_n, inlier_th))
-    return R, t, counts, best, mask
+    """lines 294-311 of models/BUFFER.py for one pair in one fused call (no R / t in memory, no .cpu() at :311):
+    -> inlier_num [A] int32, best_ind [1] int64, inlier_ind [A] int64 (first n_inliers entries valid), n_inliers [1] int32"""
+    A = ss_kpts.shape[0]
+    dev = ss_kpts.device
+    rec = _records(_f32c(ss_kpts, "ss_kpts"), _f32c(tt_kpts, "tt_kpts"))
+    off = torch.tensor([0, A], dtype=torch.int32).to(dev); cnt = torch.tensor([A], dtype=torch.int32).to(dev)
+    r = lrf_vote_batched(rec, off, cnt, ind, ss_R, tt_R, A, azi_n, inlier_th)
+    return r["inlier_num"][:A], r["best_ind"], r["inlier_ind"][:A], r["sub_cnt"]
+
+
+@_guard
+def pose_from_votes_batched(corr, corr_off, corr_cnt, ind, ss_R, tt_R, max_count, hypotheses=50000, dist_th=0.10, similar_th=0.8, confidence=1.0,
+                            refine_thr=0.10, refine_iters=20, seed=0, pair_id_base=0, azi_n=20, inlier_th=1 / 3, ransac_splits=None):
+    """The reference's stage flow after the inlier head, models/BUFFER.py:291-329, for P pairs in ONE call with zero host syncs:
+    LRF vote on all mutual matches -> inlier_ind compacted on the device -> RANSAC on that subset -> post_refinement on ALL matches.
+    Arguments as lrf_vote_batched.  -> T [P,4,4] float32, n_vote_inliers [P] int32 (= len(inlier_ind)), n_inliers [P] int32."""
+    corr = _f32c(corr, "corr"); ind = _f32c(ind, "ind"); ss_R = _f32c(ss_R, "ss_R"); tt_R = _f32c(tt_R, "tt_R")
+    dev = corr.device
+    rows, P = corr.shape[0], corr_cnt.numel()
+    T = torch.empty(P, 4, 4, dtype=torch.float32, device=dev)
+    nv = torch.empty(P, dtype=torch.int32, device=dev); ni = torch.empty(P, dtype=torch.int32, device=dev)
+    if ransac_splits is None:
+        ransac_splits = _default_splits(P)
+    L = _lib.lib()
+    ws = _ws(L.bfr_vote_workspace_bytes(P, rows), dev, "vote")
+    _lib.check(L.bfr_pose_from_votes_batched(corr.data_ptr(), corr_off.data_ptr(), corr_cnt.data_ptr(), P, int(max_count), rows, ind.data_ptr(),
+                                             ss_R.data_ptr(), tt_R.data_ptr(), float(azi_n), float(inlier_th), int(hypotheses), int(seed), int(pair_id_base),
+                                             float(dist_th), float(similar_th), float(confidence), float(refine_thr), int(refine_iters), int(ransac_splits),
+                                             T.data_ptr(), nv.data_ptr(), ni.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bfr_pose_from_votes_batched")
+    return T, nv, ni
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# K1 in phases: one huge pair whose rows are split over several GPUs (BASELINE config 5)
+# ---------------------------------------------------------------------------------------------------------------
+class MutualNNSplit:
+    """bfr_mutual_nn_partial -> (all-reduce MAX of the packed bests across ranks, done by the caller) -> bfr_mutual_select.
+    `packed` is an int64 view of the uint64 workspace region (untouched entries are 0); flipping bit 63 maps the unsigned order
+    onto the signed one, which is what NCCL's int64 MAX reduces."""
+
+    def __init__(self, src_des, tgt_des, src_off, tgt_off, max_M, max_N):
+        self.src_des = _f32c(src_des, "src_des"); self.tgt_des = _f32c(tgt_des, "tgt_des")
+        self.src_off, self.tgt_off, self.max_M, self.max_N = src_off, tgt_off, int(max_M), int(max_N)
+        self.P = src_off.numel() - 1
+        self.dev = self.src_des.device
+        L = _lib.lib()
+        self.nbytes = L.bfr_mutual_nn_workspace_bytes(self.P, self.max_M, self.max_N)
+        self.ws = torch.empty(self.nbytes + 1024, dtype=torch.uint8, device=self.dev)
+        import ctypes as C
+        ptr, cnt = C.c_void_p(0), C.c_size_t(0)
+        _lib.check(L.bfr_mutual_nn_packed(self.ws.data_ptr(), self.ws.numel(), self.P, self.max_M, self.max_N, C.byref(ptr), C.byref(cnt)), "bfr_mutual_nn_packed")
+        start = ptr.value - self.ws.data_ptr()
+        self.packed = self.ws[start:start + 8 * cnt.value].view(torch.int64)
+
+    def partial(self, part, nparts, col_splits=1):
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().bfr_mutual_nn_partial(self.src_des.data_ptr(), self.tgt_des.data_ptr(), self.src_off.data_ptr(), self.tgt_off.data_ptr(), self.P,
+                                                        self.max_M, self.max_N, self.src_des.shape[0], self.tgt_des.shape[0], DESC_DIM, int(col_splits),
+                                                        int(part), int(nparts), self.ws.data_ptr(), self.ws.numel(), _stream()), "bfr_mutual_nn_partial")
+        return self.packed
+
+    def all_reduce_max(self, group=None):
+        """unsigned 64-bit MAX across ranks with NCCL's signed int64 MAX (flip bit 63 before and after)"""
+        import torch.distributed as dist
+        self.packed ^= -0x8000000000000000
+        dist.all_reduce(self.packed, op=dist.ReduceOp.MAX, group=group)
+        self.packed ^= -0x8000000000000000
+
+    def select(self, src_xyz=None, tgt_xyz=None, want_nn=True, want_mids=True):
+        dev, P = self.dev, self.P
+        totM, totN = self.src_des.shape[0], self.tgt_des.shape[0]
+        i64 = dict(dtype=torch.int64, device=dev)
+        out = {"nn_s": torch.empty(totM, **i64) if want_nn else None, "nn_t": torch.empty(totN, **i64) if want_nn else None,
+               "s_mids": torch.empty(totM, **i64) if want_mids else None, "t_mids": torch.empty(totM, **i64) if want_mids else None,
+               "n_mutual": torch.empty(P, dtype=torch.int32, device=dev), "corr": None}
+        if src_xyz is not None:
+            src_xyz = _f32c(src_xyz, "src_xyz"); tgt_xyz = _f32c(tgt_xyz, "tgt_xyz")
+            out["corr"] = torch.empty(max(totM, 1), 8, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().bfr_mutual_select(self.src_off.data_ptr(), self.tgt_off.data_ptr(), P, self.max_M, self.max_N, _ptr(out["nn_s"]), _ptr(out["nn_t"]), 0, 0,
+                                                    _ptr(src_xyz), _ptr(tgt_xyz), _ptr(out["s_mids"]), _ptr(out["t_mids"]), out["n_mutual"].data_ptr(), _ptr(out["corr"]),
+                                                    self.ws.data_ptr(), self.ws.numel(), _stream()), "bfr_mutual_select")
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------------
 # whole back end
 # ---------------------------------------------------------------------------------------------------------------
+@_guard
 def register_batched(src_des, src_xyz, src_off, tgt_des, tgt_xyz, tgt_off, max_M, max_N, hypotheses=50000, dist_th=0.10, similar_th=0.8,
-                     refine_thr=0.10, refine_iters=20, seed=0, pair_id_base=0, ransac_splits=None):
-    """mutual matching -> RANSAC on all mutual matches -> post-refinement for P pairs, one C call, no host sync.
-    -> T [P,4,4] float32, n_mutual [P] int32, n_inliers [P] int32 (device)."""
+                     refine_thr=0.10, refine_iters=20, seed=0, pair_id_base=0, ransac_splits=None, confidence=1.0):
+    """mutual matching -> RANSAC on ALL mutual matches -> post-refinement for P pairs, one C call, no host sync.
+    -> T [P,4,4] float32, n_mutual [P] int32, n_inliers [P] int32 (device).
+    This is the test branch of buffer.forward WITHOUT the learned inlier head: the reference hands RANSAC only the LRF-vote
+    subset (models/BUFFER.py:303-316).  With the head in the loop use mutual_matching_batched -> (head) ->
+    pose_from_votes_batched, which reproduces the reference's flow exactly."""
     src_des = _f32c(src_des, "src_des"); tgt_des = _f32c(tgt_des, "tgt_des"); src_xyz = _f32c(src_xyz, "src_xyz"); tgt_xyz = _f32c(tgt_xyz, "tgt_xyz")
     dev = src_des.device
     P = src_off.numel() - 1
@@ -373,12 +532,12 @@ def register_batched(src_des, src_xyz, src_off, tgt_des, tgt_xyz, tgt_off, max_M
     T = torch.empty(P, 4, 4, dtype=torch.float32, device=dev)
     nm = torch.empty(P, dtype=torch.int32, device=dev); ni = torch.empty(P, dtype=torch.int32, device=dev)
     if ransac_splits is None:
-        ransac_splits = max(1, min(64, (296 + P - 1) // max(P, 1)))
+        ransac_splits = _default_splits(P)
     L = _lib.lib()
     ws = _ws(L.bfr_register_workspace_bytes(P, max_M, max_N, totM, totN), dev, "register")
     _lib.check(L.bfr_register_batched(src_des.data_ptr(), src_xyz.data_ptr(), src_off.data_ptr(), tgt_des.data_ptr(), tgt_xyz.data_ptr(),
                                       tgt_off.data_ptr(), P, max_M, max_N, totM, totN, DESC_DIM, int(hypotheses), int(seed), int(pair_id_base),
-                                      float(dist_th), float(similar_th), float(refine_thr), int(refine_iters), int(ransac_splits),
+                                      float(dist_th), float(similar_th), float(confidence), float(refine_thr), int(refine_iters), int(ransac_splits),
                                       T.data_ptr(), nm.data_ptr(), ni.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bfr_register_batched")
     return T, nm, ni
 
@@ -400,10 +559,11 @@ class HostRegistrar:
     This is the call bench.py times for the `e2e` number."""
 
     def __init__(self, chunk_pairs, M, N, device, hypotheses=50000, dist_th=0.10, similar_th=0.8, refine_thr=0.10, refine_iters=20,
-                 seed=0, ransac_splits=None, n_streams=2):
+                 seed=0, ransac_splits=None, n_streams=2, confidence=1.0):
         self.chunk, self.M, self.N, self.dev = chunk_pairs, M, N, torch.device(device)
-        self.kw = dict(hypotheses=hypotheses, dist_th=dist_th, similar_th=similar_th, refine_thr=refine_thr, refine_iters=refine_iters, seed=seed)
-        self.splits = ransac_splits if ransac_splits is not None else max(1, min(64, (296 + chunk_pairs - 1) // chunk_pairs))
+        self.kw = dict(hypotheses=hypotheses, dist_th=dist_th, similar_th=similar_th, refine_thr=refine_thr, refine_iters=refine_iters, seed=seed,
+                       confidence=confidence)
+        self.splits = ransac_splits if ransac_splits is not None else _default_splits(chunk_pairs)
         L = _lib.lib()
         nbytes = L.bfr_register_host_workspace_bytes(chunk_pairs, M, N, DESC_DIM)
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_streams)]
@@ -412,6 +572,10 @@ class HostRegistrar:
     def run(self, src_des, src_xyz, tgt_des, tgt_xyz, T_out, n_mutual_out=None, n_inliers_out=None):
         """all arguments are HOST tensors ([P,M,32], [P,M,3], [P,N,32], [P,N,3] float32; outputs [P,4,4] float32 and
         optional [P] int32), ideally pinned.  Returns after everything has landed in the output tensors."""
+        with torch.cuda.device(self.dev):
+            return self._run(src_des, src_xyz, tgt_des, tgt_xyz, T_out, n_mutual_out, n_inliers_out)
+
+    def _run(self, src_des, src_xyz, tgt_des, tgt_xyz, T_out, n_mutual_out, n_inliers_out):
         L = _lib.lib()
         P = src_des.shape[0]
         k = self.kw
@@ -424,7 +588,7 @@ class HostRegistrar:
             ws = self.ws[ci % len(self.streams)]
             _lib.check(L.bfr_register_uniform_host(src_des[p0].data_ptr(), src_xyz[p0].data_ptr(), tgt_des[p0].data_ptr(), tgt_xyz[p0].data_ptr(),
                                                    n, self.M, self.N, DESC_DIM, int(k["hypotheses"]), int(k["seed"]), int(p0),
-                                                   float(k["dist_th"]), float(k["similar_th"]), float(k["refine_thr"]), int(k["refine_iters"]),
+                                                   float(k["dist_th"]), float(k["similar_th"]), float(k["confidence"]), float(k["refine_thr"]), int(k["refine_iters"]),
                                                    int(self.splits), T_out[p0].data_ptr(),
                                                    0 if n_mutual_out is None else n_mutual_out[p0:].data_ptr(),
                                                    0 if n_inliers_out is None else n_inliers_out[p0:].data_ptr(),

@@ -41,7 +41,7 @@ inline RegWs reg_ws_carve(void* ws, int P, int max_M, int max_N, int total_M)
 extern "C" {
 #pragma GCC visibility push(default)
 
-int bfr_version(void) { return 100; }
+int bfr_version(void) { return 200; }
 
 const char* bfr_error_string(int code)
 {
@@ -76,6 +76,44 @@ int bfr_mutual_matching_batched(const float* src_des, const float* tgt_des, cons
                         src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, corr_xyz, st(stream)));
 }
 
+int bfr_mutual_nn_partial(const float* src_des, const float* tgt_des, const int32_t* src_off, const int32_t* tgt_off,
+                          int P, int max_M, int max_N, int total_M, int total_N, int D, int col_splits, int part, int nparts,
+                          void* ws, size_t ws_bytes, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!src_des || !tgt_des || !src_off || !tgt_off || !ws) return BFR_E_NULL;
+    if (P < 0 || P > BFR_MAX_PAIRS || max_M < 0 || max_N < 0 || total_M < 0 || total_N < 0 || nparts < 1 || part < 0 || part >= nparts) return BFR_E_SIZE;
+    if (D != 32) return BFR_E_DIM;
+    if (!aligned16(src_des) || !aligned16(tgt_des)) return BFR_E_ALIGN;
+    if (ws_bytes < k1_workspace_bytes(P, max_M, max_N)) return BFR_E_WORKSPACE;
+    return cu(k1_partial_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, total_M, total_N, D, col_splits, part, nparts, ws, st(stream)));
+}
+
+int bfr_mutual_nn_packed(void* ws, size_t ws_bytes, int P, int max_M, int max_N, uint64_t** packed, size_t* count)
+{
+    if (!ws || !packed || !count) return BFR_E_NULL;
+    if (P < 0 || max_M < 0 || max_N < 0) return BFR_E_SIZE;
+    if (ws_bytes < k1_workspace_bytes(P, max_M, max_N)) return BFR_E_WORKSPACE;
+    unsigned long long* ptr = nullptr;
+    k1_packed_view(ws, P, max_M, max_N, &ptr, count);
+    *packed = reinterpret_cast<uint64_t*>(ptr);
+    return BFR_OK;
+}
+
+int bfr_mutual_select(const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+                      int64_t* nn_s, int64_t* nn_t, float* dist_s, float* dist_t,
+                      const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr_xyz,
+                      void* ws, size_t ws_bytes, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!src_off || !tgt_off || !ws) return BFR_E_NULL;
+    if (P < 0 || P > BFR_MAX_PAIRS || max_M < 0 || max_N < 0) return BFR_E_SIZE;
+    if (ws_bytes < k1_workspace_bytes(P, max_M, max_N)) return BFR_E_WORKSPACE;
+    if (corr_xyz && (!src_xyz || !tgt_xyz)) return BFR_E_NULL;
+    if ((s_mids == nullptr) != (t_mids == nullptr)) return BFR_E_NULL;
+    return cu(k1_select_launch(src_off, tgt_off, P, max_M, max_N, ws, nn_s, nn_t, dist_s, dist_t, src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, corr_xyz, st(stream)));
+}
+
 int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr_xyz, void* stream)
 {
     if (K == 0) return BFR_OK;
@@ -86,13 +124,13 @@ int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s
 
 int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
                        uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
-                       float dist_th, float similar_th, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream)
+                       float dist_th, float similar_th, float confidence, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream)
 {
     if (P == 0) return BFR_OK;
     if (!corr_xyz || !corr_off || !corr_cnt || !best_packed) return BFR_E_NULL;
     if (P < 0 || P > BFR_MAX_PAIRS || h_end < h_begin) return BFR_E_SIZE;
     if (!aligned16(corr_xyz)) return BFR_E_ALIGN;
-    return cu(ransac_launch(corr_xyz, corr_off, corr_cnt, P, seed, pair_id_base, h_begin, h_end, dist_th, similar_th, splits,
+    return cu(ransac_launch(corr_xyz, corr_off, corr_cnt, P, seed, pair_id_base, h_begin, h_end, dist_th, similar_th, confidence, splits,
                             reinterpret_cast<unsigned long long*>(best_packed), valid_count, st(stream)));
 }
 
@@ -130,6 +168,72 @@ int bfr_score_hypotheses(const float* R, const float* t, int H, const float* src
                                       best_idx, mask, ws, st(stream)));
 }
 
+namespace {
+struct VoteWs { unsigned long long* vote_best; unsigned long long* best; int32_t* sub_cnt; float* T0; float* sub_corr; };
+inline size_t vote_ws_bytes(int P, int total_rows)
+{
+    return 2 * up256((size_t)P * 8) + up256((size_t)P * 4) + up256((size_t)P * 64) + up256((size_t)(total_rows > 0 ? total_rows : 1) * 32) + 256;
+}
+inline VoteWs vote_ws_carve(void* ws, int P)
+{
+    unsigned char* w = reinterpret_cast<unsigned char*>(up256((size_t)(uintptr_t)ws));
+    VoteWs v;
+    v.vote_best = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)P * 8);
+    v.best = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)P * 8);
+    v.sub_cnt = reinterpret_cast<int32_t*>(w); w += up256((size_t)P * 4);
+    v.T0 = reinterpret_cast<float*>(w); w += up256((size_t)P * 64);
+    v.sub_corr = reinterpret_cast<float*>(w);
+    return v;
+}
+}  // namespace
+
+size_t bfr_vote_workspace_bytes(int P, int total_rows) { return vote_ws_bytes(P < 0 ? 0 : P, total_rows); }
+
+int bfr_lrf_vote_batched(float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P, int max_count, int total_rows,
+                         const float* ind, const float* ss_R, const float* tt_R, float azi_n, float inlier_th,
+                         int32_t* inlier_num, int64_t* best_ind, float* sub_corr, int32_t* sub_cnt, int64_t* inlier_ind,
+                         void* ws, size_t ws_bytes, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!corr_xyz || !corr_off || !corr_cnt || !ind || !ss_R || !tt_R || !sub_corr || !sub_cnt || !ws) return BFR_E_NULL;
+    if (P < 0 || P > BFR_MAX_PAIRS || max_count < 0 || total_rows < 0 || !(azi_n > 0.0f)) return BFR_E_SIZE;
+    if (!aligned16(corr_xyz) || !aligned16(sub_corr)) return BFR_E_ALIGN;
+    if (ws_bytes < vote_ws_bytes(P, 0)) return BFR_E_WORKSPACE;
+    VoteWs v = vote_ws_carve(ws, P);
+    return cu(lrf_vote_launch(corr_xyz, corr_off, corr_cnt, P, max_count, ind, ss_R, tt_R, azi_n, inlier_th, inlier_num, v.vote_best, sub_corr, sub_cnt,
+                              best_ind, inlier_ind, st(stream)));
+}
+
+int bfr_pose_from_votes_batched(float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P, int max_count, int total_rows,
+                                const float* ind, const float* ss_R, const float* tt_R, float azi_n, float inlier_th,
+                                int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th, float confidence,
+                                float refine_thr, int refine_iters, int ransac_splits,
+                                float* T_out, int32_t* n_vote_inliers, int32_t* n_inliers, void* ws, size_t ws_bytes, void* stream)
+{
+    if (P == 0) return BFR_OK;
+    if (!corr_xyz || !corr_off || !corr_cnt || !ind || !ss_R || !tt_R || !T_out || !ws) return BFR_E_NULL;
+    if (P < 0 || P > BFR_MAX_PAIRS || max_count < 0 || total_rows < 0 || hypotheses < 0 || refine_iters < 0 || !(azi_n > 0.0f)) return BFR_E_SIZE;
+    if (!aligned16(corr_xyz)) return BFR_E_ALIGN;
+    if (ws_bytes < vote_ws_bytes(P, total_rows)) return BFR_E_WORKSPACE;
+    cudaStream_t s = st(stream);
+    VoteWs v = vote_ws_carve(ws, P);
+    int32_t* sub_cnt = n_vote_inliers ? n_vote_inliers : v.sub_cnt;
+    cudaError_t e = cudaMemsetAsync(v.best, 0, (size_t)P * 8, s);
+    if (e != cudaSuccess) return (int)e;
+    // models/BUFFER.py:294-311: LRF vote -> inlier_ind (compacted on device) ...
+    e = lrf_vote_launch(corr_xyz, corr_off, corr_cnt, P, max_count, ind, ss_R, tt_R, azi_n, inlier_th, nullptr, v.vote_best, v.sub_corr, sub_cnt, nullptr, nullptr, s);
+    if (e != cudaSuccess) return (int)e;
+    // ... :313-326: RANSAC on that subset ...
+    e = ransac_launch(v.sub_corr, corr_off, sub_cnt, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, confidence, ransac_splits, v.best, nullptr, s);
+    if (e != cudaSuccess) return (int)e;
+    float* T_ransac = refine_iters > 0 ? v.T0 : T_out;
+    e = ransac_finalize_launch(v.sub_corr, corr_off, sub_cnt, P, seed, pair_id_base, dist_th, similar_th, v.best, T_ransac, n_inliers, nullptr, s);
+    if (e != cudaSuccess) return (int)e;
+    // ... :327-329: post_refinement on ALL mutual matches
+    if (refine_iters > 0) e = post_refinement_launch(v.T0, corr_xyz, corr_off, corr_cnt, P, refine_thr, refine_iters, T_out, nullptr, nullptr, max_count, s);
+    return cu(e);
+}
+
 int bfr_rigid_transform_3d(const float* A, const float* B, const float* w, int bs, int n, float weight_threshold, float* T, void* stream)
 {
     if (bs == 0) return BFR_OK;
@@ -139,12 +243,12 @@ int bfr_rigid_transform_3d(const float* A, const float* B, const float* w, int b
 }
 
 int bfr_post_refinement_batched(const float* T0, const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
-                                float thr, int max_iter, float* T_out, int32_t* iters, int32_t* inliers, void* stream)
+                                float thr, int max_iter, int max_count, float* T_out, int32_t* iters, int32_t* inliers, void* stream)
 {
     if (P == 0) return BFR_OK;
     if (!T0 || !corr_xyz || !corr_off || !corr_cnt || !T_out) return BFR_E_NULL;
     if (P < 0 || max_iter < 0) return BFR_E_SIZE;
-    return cu(post_refinement_launch(T0, corr_xyz, corr_off, corr_cnt, P, thr, max_iter, T_out, iters, inliers, st(stream)));
+    return cu(post_refinement_launch(T0, corr_xyz, corr_off, corr_cnt, P, thr, max_iter, T_out, iters, inliers, max_count, st(stream)));
 }
 
 size_t bfr_register_workspace_bytes(int P, int max_M, int max_N, int total_M, int total_N)
@@ -156,14 +260,14 @@ size_t bfr_register_workspace_bytes(int P, int max_M, int max_N, int total_M, in
 int bfr_register_batched(const float* src_des, const float* src_xyz, const int32_t* src_off,
                          const float* tgt_des, const float* tgt_xyz, const int32_t* tgt_off,
                          int P, int max_M, int max_N, int total_M, int total_N, int D,
-                         int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th,
+                         int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th, float confidence,
                          float refine_thr, int refine_iters, int ransac_splits,
                          float* T_out, int32_t* n_mutual, int32_t* n_inliers, void* ws, size_t ws_bytes, void* stream)
 {
     (void)total_N;
     if (P == 0) return BFR_OK;
     if (!src_des || !src_xyz || !src_off || !tgt_des || !tgt_xyz || !tgt_off || !T_out || !n_mutual || !ws) return BFR_E_NULL;
-    if (P < 0 || P > BFR_MAX_PAIRS || max_M < 0 || max_N < 0 || total_M < 0 || hypotheses < 0 || refine_iters < 0) return BFR_E_SIZE;
+    if (P < 0 || P > BFR_MAX_PAIRS || max_M < 0 || max_N < 0 || total_M < 0 || total_N < 0 || hypotheses < 0 || refine_iters < 0) return BFR_E_SIZE;
     if (D != 32) return BFR_E_DIM;
     if (!aligned16(src_des) || !aligned16(tgt_des)) return BFR_E_ALIGN;
     if (ws_bytes < reg_ws_bytes(P, max_M, max_N, total_M)) return BFR_E_WORKSPACE;
@@ -174,12 +278,12 @@ int bfr_register_batched(const float* src_des, const float* src_xyz, const int32
     e = k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, total_M, total_N, D, 1, w.k1, nullptr, nullptr, nullptr, nullptr,
                   src_xyz, tgt_xyz, nullptr, nullptr, n_mutual, w.corr, s);
     if (e != cudaSuccess) return (int)e;
-    e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, ransac_splits, w.best, nullptr, s);
+    e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, confidence, ransac_splits, w.best, nullptr, s);
     if (e != cudaSuccess) return (int)e;
     float* T_ransac = refine_iters > 0 ? w.T0 : T_out;
     e = ransac_finalize_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, dist_th, similar_th, w.best, T_ransac, n_inliers, nullptr, s);
     if (e != cudaSuccess) return (int)e;
-    if (refine_iters > 0) e = post_refinement_launch(w.T0, w.corr, src_off, n_mutual, P, refine_thr, refine_iters, T_out, nullptr, nullptr, s);
+    if (refine_iters > 0) e = post_refinement_launch(w.T0, w.corr, src_off, n_mutual, P, refine_thr, refine_iters, T_out, nullptr, nullptr, max_M < max_N ? max_M : max_N, s);
     return cu(e);
 }
 
@@ -187,18 +291,20 @@ size_t bfr_register_host_workspace_bytes(int P, int M, int N, int D)
 {
     if (P < 0 || M < 0 || N < 0 || D < 0) return 0;
     const size_t tm = (size_t)P * M, tn = (size_t)P * N;
+    if (tm > (size_t)INT32_MAX || tn > (size_t)INT32_MAX) return 0;      // row offsets are int32 (bfr_register_uniform_host returns BFR_E_SIZE)
     return reg_ws_bytes(P, M, N, (int)tm) + up256(tm * D * 4) + up256(tn * D * 4) + up256(tm * 12) + up256(tn * 12) +
            2 * up256((size_t)(P + 1) * 4) + up256((size_t)P * 64) + 2 * up256((size_t)P * 4) + 512;
 }
 
 int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_host, const float* tgt_des_host, const float* tgt_xyz_host,
                               int P, int M, int N, int D, int hypotheses, uint64_t seed, uint32_t pair_id_base,
-                              float dist_th, float similar_th, float refine_thr, int refine_iters, int ransac_splits,
+                              float dist_th, float similar_th, float confidence, float refine_thr, int refine_iters, int ransac_splits,
                               float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host, void* ws, size_t ws_bytes, void* stream)
 {
     if (P == 0) return BFR_OK;
     if (!src_des_host || !src_xyz_host || !tgt_des_host || !tgt_xyz_host || !T_out_host || !ws) return BFR_E_NULL;
     if (P < 0 || P > BFR_MAX_PAIRS || M < 0 || N < 0) return BFR_E_SIZE;
+    if ((size_t)P * M > (size_t)INT32_MAX || (size_t)P * N > (size_t)INT32_MAX) return BFR_E_SIZE;     // int32 row offsets: checked before any copy is queued
     if (D != 32) return BFR_E_DIM;
     if (ws_bytes < bfr_register_host_workspace_bytes(P, M, N, D)) return BFR_E_WORKSPACE;
     cudaStream_t s = st(stream);
@@ -221,7 +327,7 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
     uniform_offsets_kernel<<<(P + 256) / 256, 256, 0, s>>>(d_offm, d_offn, P, M, N);
     const size_t inner = reg_ws_bytes(P, M, N, (int)tm);
     int rc = bfr_register_batched(d_sdes, d_sxyz, d_offm, d_tdes, d_txyz, d_offn, P, M, N, (int)tm, (int)tn, D, hypotheses, seed, pair_id_base,
-                                  dist_th, similar_th, refine_thr, refine_iters, ransac_splits, d_T, d_nm, d_ni, w, inner, stream);
+                                  dist_th, similar_th, confidence, refine_thr, refine_iters, ransac_splits, d_T, d_nm, d_ni, w, inner, stream);
     if (rc != BFR_OK) return rc;
     if ((e = cudaMemcpyAsync(T_out_host, d_T, (size_t)P * 64, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;
     if (n_mutual_host && (e = cudaMemcpyAsync(n_mutual_host, d_nm, (size_t)P * 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return (int)e;

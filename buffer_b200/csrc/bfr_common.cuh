@@ -138,13 +138,15 @@ BFR_DEVINL bool kabsch_rotation(const float H[9], float R[9])
     float n2[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) n2[k] = __fmaf_rn(W[2][k], W[2][k], __fmaf_rn(W[1][k], W[1][k], __fmul_rn(W[0][k], W[0][k])));
-    int i1 = 0;
-    if (n2[1] > n2[i1]) i1 = 1;
-    if (n2[2] > n2[i1]) i1 = 2;
+    // largest and second-largest column norms, selected with compares only (run-time indexing of n2[] would put it in local memory)
+    int i1 = 0; float m1 = n2[0];
+    if (n2[1] > m1) { i1 = 1; m1 = n2[1]; }
+    if (n2[2] > m1) { i1 = 2; m1 = n2[2]; }
     const int ia = (i1 == 0) ? 1 : 0, ib = (i1 == 2) ? 1 : 2;
-    const int i2 = (n2[ib] > n2[ia]) ? ib : ia;
-    // select columns without dynamic register indexing
-    float w1[3], w2[3], v1[3], v2[3], m1, m2;
+    const float na = (i1 == 0) ? n2[1] : n2[0], nb = (i1 == 2) ? n2[1] : n2[2];
+    const int i2 = (nb > na) ? ib : ia;
+    const float m2 = (nb > na) ? nb : na;
+    float w1[3], w2[3], v1[3], v2[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         w1[r] = (i1 == 0) ? W[r][0] : (i1 == 1) ? W[r][1] : W[r][2];
@@ -152,8 +154,6 @@ BFR_DEVINL bool kabsch_rotation(const float H[9], float R[9])
         w2[r] = (i2 == 0) ? W[r][0] : (i2 == 1) ? W[r][1] : W[r][2];
         v2[r] = (i2 == 0) ? V[r][0] : (i2 == 1) ? V[r][1] : V[r][2];
     }
-    m1 = (i1 == 0) ? n2[0] : (i1 == 1) ? n2[1] : n2[2];
-    m2 = (i2 == 0) ? n2[0] : (i2 == 1) ? n2[1] : n2[2];
     const float s1 = __fsqrt_rn(m1), s2 = __fsqrt_rn(m2);
     if (!(s2 > __fmul_rn(1e-6f, s1)) || !(s1 > 0.0f)) {
 #pragma unroll
@@ -197,14 +197,9 @@ BFR_DEVINL void load_sample(const float4* __restrict__ corr, const uint32_t id[3
         s[i][0] = a.x; s[i][1] = a.y; s[i][2] = a.z; q[i][0] = b.x; q[i][1] = b.y; q[i][2] = b.z;
     }
 }
-// stage 1 (cheap, every hypothesis): Philox sample, repeated-index rejection, CorrespondenceCheckerBasedOnEdgeLength on
-// squared lengths of the pairs (0,1),(0,2),(1,2)
-BFR_DEVINL bool hypothesis_precheck(const float4* __restrict__ corr, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h, float sim_th2,
-                                    uint32_t id[3], float s[3][3], float q[3][3])
+// CorrespondenceCheckerBasedOnEdgeLength on squared lengths of the sample pairs (0,1),(0,2),(1,2)
+BFR_DEVINL bool edge_lengths_ok(const float s[3][3], const float q[3][3], float sim_th2)
 {
-    sample3(seed, pair_id, h, K, id);
-    if (id[0] == id[1] || id[0] == id[2] || id[1] == id[2]) return false;
-    load_sample(corr, id, s, q);
 #pragma unroll
     for (int e = 0; e < 3; ++e) {
         const int a = (e == 2) ? 1 : 0, b = (e == 0) ? 1 : 2;
@@ -215,6 +210,15 @@ BFR_DEVINL bool hypothesis_precheck(const float4* __restrict__ corr, uint32_t K,
         if (ds2 < __fmul_rn(dt2, sim_th2) || dt2 < __fmul_rn(ds2, sim_th2)) return false;
     }
     return true;
+}
+// stage 1 (cheap, every hypothesis): Philox sample, repeated-index rejection, edge-length checker
+BFR_DEVINL bool hypothesis_precheck(const float4* __restrict__ corr, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h, float sim_th2,
+                                    uint32_t id[3], float s[3][3], float q[3][3])
+{
+    sample3(seed, pair_id, h, K, id);
+    if (id[0] == id[1] || id[0] == id[2] || id[1] == id[2]) return false;
+    load_sample(corr, id, s, q);
+    return edge_lengths_ok(s, q, sim_th2);
 }
 // stage 2 (survivors of stage 1): 3-point Kabsch + CorrespondenceCheckerBasedOnDistance on the three samples
 BFR_DEVINL bool hypothesis_fit(const float s[3][3], const float q[3][3], float dist_th2, float R[9], float t[3])
@@ -250,6 +254,70 @@ BFR_DEVINL bool make_hypothesis(const float4* __restrict__ corr, uint32_t K, uin
     uint32_t id[3]; float s[3][3], q[3][3];
     if (!hypothesis_precheck(corr, K, seed, pair_id, h, sim_th2, id, s, q)) return false;
     return hypothesis_fit(s, q, dist_th2, R, t);
+}
+
+// ---- helpers with a bit-pinned CPU twin in oracle/bfr_oracle.c -----------------------------------------------------------
+// sqrt_rn(d2) < thr  <=>  d2 < sqrt_threshold(thr): the smallest float whose correctly rounded square root reaches thr (sqrt_rn is
+// monotone).  Lets the scoring loops keep a squared-distance compare while counting exactly what the reference's
+// `torch.sqrt(d2) < thr` counts (models/BUFFER.py:305-308).  thr <= 0 or NaN: nothing is ever an inlier.
+BFR_DEVINL float sqrt_threshold(float thr)
+{
+    if (!(thr > 0.0f)) return 0.0f;
+    if (thr == __int_as_float(0x7f800000)) return thr;
+    float x = __fmul_rn(thr, thr);
+    if (x == __int_as_float(0x7f800000)) x = 3.402823466e38f;
+    if (__fsqrt_rn(3.402823466e38f) < thr) return __int_as_float(0x7f800000);     // every finite d2 passes
+    while (x > 0.0f && __fsqrt_rn(__uint_as_float(__float_as_uint(x) - 1u)) >= thr) x = __uint_as_float(__float_as_uint(x) - 1u);
+    while (__fsqrt_rn(x) < thr) x = __uint_as_float(__float_as_uint(x) + 1u);
+    return x;
+}
+
+// sin / cos of a non-negative angle with nothing but fma / mul / rint (Cody-Waite reduction by pi/2 in three parts, Cephes minimax
+// polynomials on [-pi/4, pi/4]); max error ~1.2e-7 for angles up to a few hundred.  Used for the LRF angle of models/BUFFER.py:295.
+BFR_DEVINL void det_sincos(float a, float& sn, float& cs)
+{
+    const float k = rintf(__fmul_rn(a, 0.63661977236758134f));
+    float r = __fmaf_rn(-k, 1.5703125f, a);
+    r = __fmaf_rn(-k, 4.837512969970703125e-4f, r);
+    r = __fmaf_rn(-k, 7.54978995489188e-8f, r);
+    const float z = __fmul_rn(r, r);
+    float ps = __fmaf_rn(z, -1.9515295891e-4f, 8.3321608736e-3f);
+    ps = __fmaf_rn(z, ps, -1.6666654611e-1f);
+    const float s = __fmaf_rn(__fmul_rn(z, r), ps, r);
+    float pc = __fmaf_rn(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    pc = __fmaf_rn(z, pc, 4.166664568298827e-2f);
+    const float c = __fmaf_rn(__fmul_rn(z, z), pc, __fmaf_rn(-0.5f, z, 1.0f));
+    const int q = ((int)k) & 3;
+    sn = (q == 0) ? s : (q == 1) ? c : (q == 2) ? -s : -c;
+    cs = (q == 0) ? c : (q == 1) ? -s : (q == 2) ? -c : s;
+}
+
+// natural logarithm of a positive finite double from + - * / fma only (exact exponent split, atanh series): every step is a
+// correctly rounded IEEE operation, so the CPU oracle reproduces it bit for bit.  Used for Open3D's RANSAC iteration bound.
+BFR_DEVINL double det_log(double v)
+{
+    long long bits = __double_as_longlong(v);
+    int e = (int)((bits >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);     // [1, 2)
+    if (m > 1.4142135623730951) { m = __dmul_rn(m, 0.5); e += 1; }
+    const double y = __ddiv_rn(__dsub_rn(m, 1.0), __dadd_rn(m, 1.0)), y2 = __dmul_rn(y, y);
+    double p = 1.0 / 27.0;
+#pragma unroll
+    for (int k = 25; k >= 1; k -= 2) p = __fma_rn(p, y2, 1.0 / (double)k);
+    return __fma_rn((double)e, 0.6931471805599453, __dmul_rn(__dmul_rn(2.0, y), p));
+}
+// Open3D RANSACConvergenceCriteria: iterations allowed once a hypothesis with `count` inliers of K is the best:
+// min(max_iter, ceil(log(1 - confidence) / log(1 - (count / K)^3)))
+BFR_DEVINL uint32_t ransac_exit_bound(uint32_t count, uint32_t K, double log_1m_conf, uint32_t max_iter)
+{
+    if (count == 0u || K == 0u) return max_iter;
+    const double x = __ddiv_rn((double)count, (double)K), x3 = __dmul_rn(__dmul_rn(x, x), x);
+    if (!(x3 < 1.0)) return 0u;
+    const double den = det_log(__dsub_rn(1.0, x3));
+    if (!(den < 0.0)) return max_iter;
+    const double b = ceil(__ddiv_rn(log_1m_conf, den));
+    if (!(b < (double)max_iter)) return max_iter;
+    return b < 0.0 ? 0u : (uint32_t)b;
 }
 
 }  // namespace bfr

@@ -16,6 +16,7 @@
 // with a 64-bit atomicMax.  Issue-slot accounting and the measured roofline are in DESIGN.md §K1.
 #include "bfr_common.cuh"
 #include "bfr_kernels.h"
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 
@@ -167,15 +168,15 @@ __global__ void __launch_bounds__(K1_THREADS, 2)
 k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
                     const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
                     const float* __restrict__ hna, const float* __restrict__ hnb, int padM, int padN,
-                    unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_packed, int splits)
+                    unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_packed, int splits, int blk0)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Smem& sm = *reinterpret_cast<K1Smem*>(smem_raw);
 
     const int p = blockIdx.z;
-    const int so = src_off[p], M = src_off[p + 1] - so;
-    const int to = tgt_off[p], N = tgt_off[p + 1] - to;
-    const int row0 = blockIdx.x * K1_ROWS;
+    const int so = src_off[p], M = min(src_off[p + 1] - so, padM);     // a pair larger than the caller's max_M / max_N bound is truncated to it,
+    const int to = tgt_off[p], N = min(tgt_off[p + 1] - to, padN);     // never read past its workspace slice
+    const int row0 = (blk0 + (int)blockIdx.x) * K1_ROWS;
     if (row0 >= M || N <= 0) return;
     const int ntiles = (N + K1_TILE - 1) / K1_TILE;
     const int t_begin = (int)(((long long)blockIdx.y * ntiles) / splits);
@@ -260,45 +261,93 @@ k1_mutual_nn_kernel(const float* __restrict__ src, const float* __restrict__ tgt
 }
 
 // ---- select: decode packed bests, mutual check, ascending compaction, optional gather of matched keypoints --------
-// One CTA per pair.  Mirrors models/BUFFER.py:356-357 (s_mids ascending, t_mids = nn_s[s_mids]) and :284,:287
-// (ss_kpts = kpts1[s_mids], tt_kpts = kpts2[t_mids]) written as 8-float records {sx sy sz 0 qx qy qz 0}.
-__global__ void __launch_bounds__(256) k1_select_kernel(const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
-                                                        const unsigned long long* __restrict__ row_packed, const unsigned long long* __restrict__ col_packed,
-                                                        const float* __restrict__ hna, int padM, int padN,
-                                                        int64_t* __restrict__ nn_s, int64_t* __restrict__ nn_t, float* __restrict__ d_s, float* __restrict__ d_t,
-                                                        const float* __restrict__ src_xyz, const float* __restrict__ tgt_xyz,
-                                                        int64_t* __restrict__ s_mids, int64_t* __restrict__ t_mids, int32_t* __restrict__ n_mutual,
-                                                        float4* __restrict__ corr)
+// Mirrors models/BUFFER.py:356-357 (s_mids ascending, t_mids = nn_s[s_mids]) and :284,:287 (ss_kpts = kpts1[s_mids],
+// tt_kpts = kpts2[t_mids]) written as 8-float records {sx sy sz 0 qx qy qz 0}.  Two phases so that one huge pair (BASELINE config 5:
+// 100k x 100k) is not decoded by a single CTA: k1_decode_kernel (one CTA per 1024-row block) writes nn / distances and the number of
+// mutual matches of its block; k1_compact_kernel adds up the counts of the blocks before its own (<= a few hundred ints) and scatters.
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_ROWS = 1024;                 // rows per CTA (4 per thread)
+
+BFR_DEVINL bool mutual_flag(const unsigned long long* __restrict__ rowp, const unsigned long long* __restrict__ colp, int i, int M, int N, uint32_t& j)
 {
-    __shared__ int warp_cnt[8];
+    if (i >= M) { j = 0; return false; }
+    j = packed_index(rowp[i]);
+    return (N > 0) && (j < (uint32_t)N) && (packed_index(colp[j]) == (uint32_t)i);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k1_decode_kernel(const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
+                                                                const unsigned long long* __restrict__ row_packed, const unsigned long long* __restrict__ col_packed,
+                                                                const float* __restrict__ hna, int padM, int padN, int nblk,
+                                                                int64_t* __restrict__ nn_s, int64_t* __restrict__ nn_t, float* __restrict__ d_s, float* __restrict__ d_t,
+                                                                int32_t* __restrict__ blk_cnt)
+{
+    __shared__ int warp_cnt[SEL_THREADS / 32];
+    const int p = blockIdx.y, b = blockIdx.x;
+    const int so = src_off[p], M = min(src_off[p + 1] - so, padM), to = tgt_off[p], N = min(tgt_off[p + 1] - to, padN);
+    const unsigned long long* rowp = row_packed + (size_t)p * padM;
+    const unsigned long long* colp = col_packed + (size_t)p * padN;
+    if (nn_t || d_t)
+        for (int j = b * SEL_ROWS + threadIdx.x; j < min(N, (b + 1) * SEL_ROWS); j += SEL_THREADS) {
+            const unsigned long long c = colp[j];
+            if (nn_t) nn_t[to + j] = (int64_t)packed_index(c);
+            if (d_t) { const float d2 = __fmul_rn(-2.0f, key_float((uint32_t)(c >> 32))); d_t[to + j] = __fsqrt_rn(d2 > 0.0f ? d2 : 0.0f); }
+        }
+    int cnt = 0;
+    for (int i = b * SEL_ROWS + threadIdx.x; i < min(M, (b + 1) * SEL_ROWS); i += SEL_THREADS) {
+        uint32_t j;
+        cnt += mutual_flag(rowp, colp, i, M, N, j) ? 1 : 0;
+        if (nn_s) nn_s[so + i] = (int64_t)j;
+        if (d_s) { const float d2 = __fmul_rn(-2.0f, __fadd_rn(key_float((uint32_t)(rowp[i] >> 32)), hna[(size_t)p * padM + i])); d_s[so + i] = __fsqrt_rn(d2 > 0.0f ? d2 : 0.0f); }
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) warp_cnt[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < SEL_THREADS / 32; ++w) tot += warp_cnt[w];
+        if (b < nblk) blk_cnt[(size_t)p * nblk + b] = tot;            // (blocks beyond the source side only decode target rows)
+    }
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) k1_compact_kernel(const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
+                                                                 const unsigned long long* __restrict__ row_packed, const unsigned long long* __restrict__ col_packed,
+                                                                 int padM, int padN, int nblk, const int32_t* __restrict__ blk_cnt,
+                                                                 const float* __restrict__ src_xyz, const float* __restrict__ tgt_xyz,
+                                                                 int64_t* __restrict__ s_mids, int64_t* __restrict__ t_mids, int32_t* __restrict__ n_mutual,
+                                                                 float4* __restrict__ corr)
+{
+    __shared__ int warp_cnt[SEL_THREADS / 32];
     __shared__ int base_s;
-    const int p = blockIdx.x;
-    const int so = src_off[p], M = src_off[p + 1] - so, to = tgt_off[p], N = tgt_off[p + 1] - to;
+    const int p = blockIdx.y, b = blockIdx.x;
+    const int so = src_off[p], M = min(src_off[p + 1] - so, padM), to = tgt_off[p], N = min(tgt_off[p + 1] - to, padN);
     const unsigned long long* rowp = row_packed + (size_t)p * padM;
     const unsigned long long* colp = col_packed + (size_t)p * padN;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        const unsigned long long c = colp[j];
-        if (nn_t) nn_t[to + j] = (int64_t)packed_index(c);
-        if (d_t) { const float d2 = __fmul_rn(-2.0f, key_float((uint32_t)(c >> 32))); d_t[to + j] = __fsqrt_rn(d2 > 0.0f ? d2 : 0.0f); }
-    }
-    if (threadIdx.x == 0) base_s = 0;
-    __syncthreads();
-    for (int i0 = 0; i0 < M; i0 += blockDim.x) {
-        const int i = i0 + threadIdx.x;
-        bool flag = false; uint32_t j = 0;
-        if (i < M) {
-            const unsigned long long r = rowp[i];
-            j = packed_index(r);
-            if (nn_s) nn_s[so + i] = (int64_t)j;
-            if (d_s) { const float d2 = __fmul_rn(-2.0f, __fadd_rn(key_float((uint32_t)(r >> 32)), hna[(size_t)p * padM + i])); d_s[so + i] = __fsqrt_rn(d2 > 0.0f ? d2 : 0.0f); }
-            flag = (N > 0) && (j < (uint32_t)N) && (packed_index(colp[j]) == (uint32_t)i);
+    {   // matches in the blocks before this one (and, for the last block, the pair's total)
+        int before = 0, total = 0;
+        for (int k = threadIdx.x; k < nblk; k += SEL_THREADS) { const int c = blk_cnt[(size_t)p * nblk + k]; total += c; if (k < b) before += c; }
+        before = __reduce_add_sync(0xffffffffu, before); total = __reduce_add_sync(0xffffffffu, total);
+        if (lane == 0) { warp_cnt[warp] = before; }
+        __syncthreads();
+        if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < SEL_THREADS / 32; ++w) s += warp_cnt[w]; base_s = s; }
+        __syncthreads();
+        if (n_mutual && b == nblk - 1) {
+            if (lane == 0) warp_cnt[warp] = total;
+            __syncthreads();
+            if (threadIdx.x == 0) { int s = 0; for (int w = 0; w < SEL_THREADS / 32; ++w) s += warp_cnt[w]; n_mutual[p] = s; }
         }
+        __syncthreads();
+    }
+    if (!s_mids && !corr) return;
+    for (int i0 = b * SEL_ROWS; i0 < min(M, (b + 1) * SEL_ROWS); i0 += SEL_THREADS) {
+        const int i = i0 + threadIdx.x;
+        uint32_t j;
+        const bool flag = mutual_flag(rowp, colp, i, M, N, j);
         const unsigned bal = __ballot_sync(0xffffffffu, flag);
         if (lane == 0) warp_cnt[warp] = __popc(bal);
         __syncthreads();
         int pre = base_s, tot = 0;
-        for (int w = 0; w < 8; ++w) { const int c = warp_cnt[w]; if (w < warp) pre += c; tot += c; }
+        for (int w = 0; w < SEL_THREADS / 32; ++w) { const int c = warp_cnt[w]; if (w < warp) pre += c; tot += c; }
         if (flag) {
             const int pos = pre + __popc(bal & ((1u << lane) - 1u));
             if (s_mids) { s_mids[so + pos] = (int64_t)i; t_mids[so + pos] = (int64_t)j; }
@@ -312,7 +361,6 @@ __global__ void __launch_bounds__(256) k1_select_kernel(const int32_t* __restric
         if (threadIdx.x == 0) base_s += tot;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && n_mutual) n_mutual[p] = base_s;
 }
 
 // gather correspondences given explicit index pairs (the Open3D-style API: pcd0, pcd1, corr)
@@ -363,65 +411,127 @@ static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 int k1_pad_rows(int max_rows) { return round_up(max_rows > 0 ? max_rows : 1, K1_ROWS); }   // multiple of 512 (and of 64)
 
+// workspace carve-up: packed u64 arrays first (one contiguous region: what a multi-GPU row split max-reduces), then the float arrays
+// (256-byte aligned for TMA), the f16 copies of the tensor-core path, the range flags and the per-block match counts of the select phase
+struct K1Ws {
+    unsigned long long* row_packed; unsigned long long* col_packed; float* hna; float* hnb; uint4* src_h; uint4* tgt_h; int32_t* oor; int32_t* blk_cnt;
+    int padM, padN, sel_blocks;
+};
+static inline int k1_sel_blocks(int padM) { return (padM + SEL_ROWS - 1) / SEL_ROWS; }
+
+static K1Ws k1_carve(void* ws, int P, int max_M, int max_N)
+{
+    K1Ws k;
+    k.padM = k1_pad_rows(max_M); k.padN = k1_pad_rows(max_N); k.sel_blocks = k1_sel_blocks(k.padM);
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)ws + 255) & ~(uintptr_t)255);
+    k.row_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * k.padM * 8;
+    k.col_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * k.padN * 8;
+    k.hna = reinterpret_cast<float*>(w); w += (size_t)P * k.padM * 4;
+    k.hnb = reinterpret_cast<float*>(w); w += (size_t)P * k.padN * 4;
+    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    k.src_h = reinterpret_cast<uint4*>(w); w += (size_t)P * k.padM * K1_D * 2;          // total_M <= P * padM rows
+    k.tgt_h = reinterpret_cast<uint4*>(w); w += (size_t)P * k.padN * K1_D * 2;
+    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    k.oor = reinterpret_cast<int32_t*>(w); w += (size_t)P * 8;                           // [2][P]: source side, target side
+    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    k.blk_cnt = reinterpret_cast<int32_t*>(w);
+    return k;
+}
+
 size_t k1_workspace_bytes(int P, int max_M, int max_N)
 {
     const size_t padM = (size_t)k1_pad_rows(max_M), padN = (size_t)k1_pad_rows(max_N);
-    // packed bests + half norms + (tensor-core path) f16 copies of both descriptor sets (<= P * pad rows of 64 bytes each) + range flags
-    return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long) + (size_t)K1_D * 2) + (size_t)P * 8 + 1024;
+    // packed bests + half norms + (tensor-core path) f16 copies of both descriptor sets (<= P * pad rows of 64 bytes each) + range flags + block counts
+    return (size_t)P * (padM + padN) * (sizeof(float) + sizeof(unsigned long long) + (size_t)K1_D * 2) + (size_t)P * 8 +
+           (size_t)P * k1_sel_blocks((int)padM) * 4 + 2048;
 }
 
-static int g_k1_algo = 1;                       // 0 = FP32 FFMA2 kernel, 1 = tensor-core filter + exact re-check (mutual_nn_tc.cu)
+void k1_packed_view(void* ws, int P, int max_M, int max_N, unsigned long long** packed, size_t* count)
+{
+    const K1Ws k = k1_carve(ws, P, max_M, max_N);
+    *packed = k.row_packed;                                           // row_packed [P * padM] immediately followed by col_packed [P * padN]
+    *count = (size_t)P * ((size_t)k.padM + (size_t)k.padN);
+}
+
+static thread_local int g_k1_algo = 1;          // 0 = FP32 FFMA2 kernel, 1 = tensor-core filter + exact re-check (mutual_nn_tc.cu); per calling thread
 void k1_set_algo(int algo) { g_k1_algo = algo; }
 int k1_get_algo() { return g_k1_algo; }
+
+cudaError_t ensure_dyn_smem(const void* fn, int bytes, std::atomic<unsigned long long>& done)
+{
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);   // a per-device attribute; setting it twice is harmless
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+
+// phase 1 + 2: half norms / f16 copies / zeroed packed bests for ALL rows, then the main kernel on row-block partition `part` of `nparts`
+// (both directions are partitioned by row blocks of their own side).  nparts = 1: the whole job.
+cudaError_t k1_partial_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+                              long long total_M, long long total_N, int D, int col_splits, int part, int nparts, void* ws, cudaStream_t stream)
+{
+    if (D != K1_D || nparts < 1 || part < 0 || part >= nparts) return cudaErrorInvalidValue;
+    const K1Ws k = k1_carve(ws, P, max_M, max_N);
+    const bool tc = g_k1_algo == 1 && max_M > 0 && max_N > 0 && k1_tc_supported(D, total_M, total_N);
+    {
+        const long long na = (long long)P * k.padM, nb = (long long)P * k.padN;
+        if (tc) { cudaError_t e = cudaMemsetAsync(k.oor, 0, (size_t)P * 8, stream); if (e != cudaSuccess) return e; }
+        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, k.padM, k.hna, k.row_packed, tc ? k.src_h : nullptr, k.oor);
+        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, k.padN, k.hnb, k.col_packed, tc ? k.tgt_h : nullptr, k.oor + P);
+    }
+    if (col_splits < 1) col_splits = 1;
+    if (g_k1_ev0) cudaEventRecord(g_k1_ev0, stream);
+    if (max_M > 0 && max_N > 0) {
+        if (tc) {
+            cudaError_t e = k1_tc_launch(src, tgt, k.src_h, k.tgt_h, k.oor, src_off, tgt_off, P, max_M, max_N, total_M, total_N, k.hna, k.hnb, k.padM, k.padN,
+                                         k.row_packed, k.col_packed, part, nparts, stream);
+            if (e != cudaSuccess) return e;
+        } else {
+            static std::atomic<unsigned long long> attr_done{0};
+            cudaError_t e = ensure_dyn_smem((const void*)k1_mutual_nn_kernel, (int)sizeof(K1Smem), attr_done);
+            if (e != cudaSuccess) return e;
+            const int nblk = (max_M + K1_ROWS - 1) / K1_ROWS;
+            const int b0 = (int)(((long long)part * nblk) / nparts), b1 = (int)(((long long)(part + 1) * nblk) / nparts);
+            if (b1 > b0) {
+                dim3 grid((unsigned)(b1 - b0), (unsigned)col_splits, (unsigned)P);
+                k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, k.hna, k.hnb, k.padM, k.padN, k.row_packed, k.col_packed,
+                                                                                  col_splits, b0);
+            }
+        }
+    }
+    if (g_k1_ev1) cudaEventRecord(g_k1_ev1, stream);
+    return cudaGetLastError();
+}
+
+// phase 3: decode the (complete) packed bests
+cudaError_t k1_select_launch(const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N, void* ws,
+                             int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t, const float* src_xyz, const float* tgt_xyz,
+                             int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr, cudaStream_t stream)
+{
+    const K1Ws k = k1_carve(ws, P, max_M, max_N);
+    const int nblk_m = k.sel_blocks, nblk_n = k1_sel_blocks(k.padN);
+    dim3 grid((unsigned)(nblk_m > nblk_n ? nblk_m : nblk_n), (unsigned)P);   // target rows beyond the source block count are decoded by extra blocks
+    k1_decode_kernel<<<grid, SEL_THREADS, 0, stream>>>(src_off, tgt_off, k.row_packed, k.col_packed, k.hna, k.padM, k.padN, nblk_m, nn_s, nn_t, d_s, d_t, k.blk_cnt);
+    if (s_mids || corr || n_mutual) {
+        dim3 grid2((unsigned)nblk_m, (unsigned)P);
+        k1_compact_kernel<<<grid2, SEL_THREADS, 0, stream>>>(src_off, tgt_off, k.row_packed, k.col_packed, k.padM, k.padN, nblk_m, k.blk_cnt, src_xyz, tgt_xyz,
+                                                             s_mids, t_mids, n_mutual, reinterpret_cast<float4*>(corr));
+    }
+    return cudaGetLastError();
+}
 
 cudaError_t k1_launch(const float* src, const float* tgt, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
                       long long total_M, long long total_N, int D, int col_splits, void* ws, int64_t* nn_s, int64_t* nn_t, float* d_s, float* d_t,
                       const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr,
                       cudaStream_t stream)
 {
-    if (D != K1_D) return cudaErrorInvalidValue;
-    const int padM = k1_pad_rows(max_M), padN = k1_pad_rows(max_N);
-    // workspace carve-up: packed u64 arrays first (8-byte aligned), then the float arrays (256-byte aligned for TMA)
-    unsigned char* w = reinterpret_cast<unsigned char*>(ws);
-    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
-    unsigned long long* row_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * padM * 8;
-    unsigned long long* col_packed = reinterpret_cast<unsigned long long*>(w); w += (size_t)P * padN * 8;
-    float* hna = reinterpret_cast<float*>(w); w += (size_t)P * padM * 4;
-    float* hnb = reinterpret_cast<float*>(w); w += (size_t)P * padN * 4;
-    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
-    uint4* src_h = reinterpret_cast<uint4*>(w); w += (size_t)P * padM * K1_D * 2;          // total_M <= P * padM rows
-    uint4* tgt_h = reinterpret_cast<uint4*>(w); w += (size_t)P * padN * K1_D * 2;
-    w = reinterpret_cast<unsigned char*>(((uintptr_t)w + 255) & ~(uintptr_t)255);
-    int32_t* oor = reinterpret_cast<int32_t*>(w);                                           // [2][P]: source side, target side
-    const bool tc = g_k1_algo == 1 && max_M > 0 && max_N > 0 && k1_tc_supported(D, total_M, total_N);
-
-    {
-        const long long na = (long long)P * padM, nb = (long long)P * padN;
-        if (tc) { cudaError_t e = cudaMemsetAsync(oor, 0, (size_t)P * 8, stream); if (e != cudaSuccess) return e; }
-        k1_prep_kernel<<<(unsigned)((na + 255) / 256), 256, 0, stream>>>(src, src_off, P, D, padM, hna, row_packed, tc ? src_h : nullptr, oor);
-        k1_prep_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, stream>>>(tgt, tgt_off, P, D, padN, hnb, col_packed, tc ? tgt_h : nullptr, oor + P);
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k1_mutual_nn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem));
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    if (col_splits < 1) col_splits = 1;
-    dim3 grid((unsigned)((max_M + K1_ROWS - 1) / K1_ROWS), (unsigned)col_splits, (unsigned)P);
-    if (g_k1_ev0) cudaEventRecord(g_k1_ev0, stream);
-    if (max_M > 0 && max_N > 0) {
-        if (tc) {
-            cudaError_t e = k1_tc_launch(src, tgt, src_h, tgt_h, oor, src_off, tgt_off, P, max_M, max_N, total_M, total_N, hna, hnb, padM, padN, row_packed, col_packed, stream);
-            if (e != cudaSuccess) return e;
-        } else {
-            k1_mutual_nn_kernel<<<grid, K1_THREADS, sizeof(K1Smem), stream>>>(src, tgt, src_off, tgt_off, hna, hnb, padM, padN, row_packed, col_packed, col_splits);
-        }
-    }
-    if (g_k1_ev1) cudaEventRecord(g_k1_ev1, stream);
-    k1_select_kernel<<<P, 256, 0, stream>>>(src_off, tgt_off, row_packed, col_packed, hna, padM, padN, nn_s, nn_t, d_s, d_t,
-                                            src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, reinterpret_cast<float4*>(corr));
-    return cudaGetLastError();
+    cudaError_t e = k1_partial_launch(src, tgt, src_off, tgt_off, P, max_M, max_N, total_M, total_N, D, col_splits, 0, 1, ws, stream);
+    if (e != cudaSuccess) return e;
+    return k1_select_launch(src_off, tgt_off, P, max_M, max_N, ws, nn_s, nn_t, d_s, d_t, src_xyz, tgt_xyz, s_mids, t_mids, n_mutual, corr, stream);
 }
 
 cudaError_t gather_corr_launch(const float* src_xyz, const float* tgt_xyz, const int64_t* s_ids, const int64_t* t_ids, int K, float* corr, cudaStream_t stream)

@@ -28,6 +28,7 @@
 #include "bfr_common.cuh"
 #include "bfr_kernels.h"
 #include <cuda.h>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <type_traits>
@@ -249,7 +250,7 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
              const int32_t* __restrict__ src_off, const int32_t* __restrict__ tgt_off,
              const float* __restrict__ hn_src, const float* __restrict__ hn_tgt, int pad_src, int pad_tgt,
              unsigned long long* __restrict__ row_packed, unsigned long long* __restrict__ col_packed,
-             const int32_t* __restrict__ out_of_range, int num_pairs, int nblk_src, int splits_src, int splits_tgt)
+             const int32_t* __restrict__ out_of_range, int num_pairs, int nblk_src, int splits_src, int splits_tgt, int blk0_src, int blk0_tgt)
 {
     extern __shared__ __align__(1024) unsigned char smem_raw[];      // no static shared memory in this kernel: base is 1024-aligned
     TcSmem& sm = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -271,9 +272,9 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
     unsigned long long* __restrict__ out_packed = COLDIR ? col_packed : row_packed;
 
     const int p = blockIdx.z;
-    const int oo = off_own[p], M = off_own[p + 1] - oo;
-    const int os = off_str[p], N = off_str[p + 1] - os;
-    const int row0 = bx * TC_BM;
+    const int oo = off_own[p], M = min(off_own[p + 1] - oo, pad_own);   // a pair larger than the caller's max_M / max_N bound is truncated to it
+    const int os = off_str[p], N = min(off_str[p + 1] - os, pad_str);
+    const int row0 = ((COLDIR ? blk0_tgt : blk0_src) + bx) * TC_BM;     // blk0_*: first row block of this launch's partition (multi-GPU row split)
     if (row0 >= M || N <= 0) return;
     // a descriptor of this pair does not fit f16 (|x| > 65504 or non-finite): the filter's scores are meaningless (inf / NaN), so every row
     // of the pair is scanned exactly by its warp.  The flags are only consumed after the main loop: their load latency costs nothing.
@@ -392,7 +393,11 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
         const float own_norm = sqrtf(fmaxf(-2.0f * own_hn, 0.0f)), str_norm = sqrtf(fmaxf(str_max_sq, 0.0f));
         // 2 eps, eps = 1.0625 * 2^-10 |a| max|b| + 2^-22 (|a| + max|b|): f16 operands carry 11 significand bits (relative error 2^-11 each),
         // or an absolute error of at most 2^-25 per element below the normal range
-        const float two_eps = 0.0020752f * own_norm * str_norm + 4.77e-7f * (own_norm + str_norm) + 1e-30f;
+        // ... plus the rounding of the exact FP32 chain itself, which defines the winner: 33 round-offs of partial sums bounded by
+        // |b|^2/2 + |a||b| <= 1.5 max(|a|, max|b|)^2 (2^-24 each) -- negligible for normalised rows, but it keeps the band airtight when a row's
+        // norm is far below the largest streamed norm
+        const float big_norm = fmaxf(own_norm, str_norm);
+        const float two_eps = 0.0020752f * own_norm * str_norm + 4.77e-7f * (own_norm + str_norm) + 6.0e-6f * big_norm * big_norm + 1e-30f;
         // Streamed norms (nearly) uniform -- L2-normalised descriptors, BUFFER's case: rank full tiles on the raw dot products
         // (no hn add) and widen the band by the spread of hn; scores of hn-adjusted (partial) tiles are shifted by -hmax to match.
         const bool uniform = hn_spread <= 0.0009765625f * str_max_sq;   // CTA-uniform (the branch below contains warp-collective TMEM loads)
@@ -685,17 +690,16 @@ bool k1_tc_supported(int D, long long total_M, long long total_N) { return D == 
 // both directions; hna/hnb/row_packed/col_packed are the (prepared, zeroed) workspace arrays of k1_launch
 cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_f16, const void* tgt_f16, const int32_t* out_of_range, const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
                          long long total_M, long long total_N, const float* hna, const float* hnb, int padM, int padN,
-                         unsigned long long* row_packed, unsigned long long* col_packed, cudaStream_t stream)
+                         unsigned long long* row_packed, unsigned long long* col_packed, int part, int nparts, cudaStream_t stream)
 {
     CUtensorMap ms_own, ms_str, mt_own, mt_str;
     if (!make_map(&ms_own, src_f16, total_M, TC_BM) || !make_map(&ms_str, src_f16, total_M, TC_BN) ||
         !make_map(&mt_own, tgt_f16, total_N, TC_BM) || !make_map(&mt_str, tgt_f16, total_N, TC_BN)) return cudaErrorNotSupported;
     const size_t smem = sizeof(TcSmem) + 1024;
-    static bool once = false;
-    if (!once) {
-        cudaError_t e = cudaFuncSetAttribute(k1_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        static std::atomic<unsigned long long> attr_done{0};
+        cudaError_t e = ensure_dyn_smem((const void*)k1_tc_kernel, (int)smem, attr_done);
         if (e != cudaSuccess) return e;
-        once = true;
     }
     // one launch, both directions: x = row blocks of the source side, then of the target side; y = column splits (the larger of the two
     // directions' counts; the other direction's surplus CTAs exit at once); z = pair
@@ -704,7 +708,10 @@ cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_f16
     // column splits: as many as the hn cache demands (TC_MAX_TILES tiles per CTA); for small batches (the reference registers one pair per
     // forward) more, so that the row blocks of one or two pairs still cover the 148 SMs in one wave (>= 4 tiles per CTA, at most 8 splits);
     // rows merge across splits through the packed RED.MAX like across CTAs
-    const long long ctas = (long long)P * (nblk_src + nblk_tgt);
+    // multi-GPU row split: this launch owns row blocks [b0, b1) of each direction (nparts = 1: all of them)
+    const int b0s = (int)(((long long)part * nblk_src) / nparts), b1s = (int)(((long long)(part + 1) * nblk_src) / nparts);
+    const int b0t = (int)(((long long)part * nblk_tgt) / nparts), b1t = (int)(((long long)(part + 1) * nblk_tgt) / nparts);
+    const long long ctas = (long long)P * ((b1s - b0s) + (b1t - b0t));
     const int fill = ctas > 0 && ctas < 148 ? (int)(148 / ctas) : 1;
     auto pick = [&](int tiles) {
         int need = (tiles + TC_MAX_TILES - 1) / TC_MAX_TILES; if (need < 1) need = 1;
@@ -713,9 +720,10 @@ cudaError_t k1_tc_launch(const float* src, const float* tgt, const void* src_f16
     };
     const int splits_src = pick(tiles_tgt);     // src rows own, tgt streamed
     const int splits_tgt = pick(tiles_src);     // tgt rows own, src streamed
-    dim3 grid((unsigned)(nblk_src + nblk_tgt), (unsigned)(splits_src > splits_tgt ? splits_src : splits_tgt), (unsigned)P);
+    if ((b1s - b0s) + (b1t - b0t) <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((b1s - b0s) + (b1t - b0t)), (unsigned)(splits_src > splits_tgt ? splits_src : splits_tgt), (unsigned)P);
     k1_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(ms_own, mt_str, mt_own, ms_str, src, tgt, src_off, tgt_off, hna, hnb, padM, padN,
-                                                     row_packed, col_packed, out_of_range, P, nblk_src, splits_src, splits_tgt);
+                                                     row_packed, col_packed, out_of_range, P, b1s - b0s, splits_src, splits_tgt, b0s, b0t);
     return cudaGetLastError();
 }
 

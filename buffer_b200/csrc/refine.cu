@@ -2,16 +2,35 @@
 //
 // Replaces rigid_transform_3d (reference models/BUFFER.py:424-464: diag_embed(weights) [n x n], Am^T W Bm and a
 // GPU->CPU->GPU torch.svd per call) and buffer.post_refinement (models/BUFFER.py:382-418: one host sync per round for
-// int(inlier_num)).  One CTA of 256 threads per pair / batch element; the weighted sums use a FIXED reduction tree
-// (lane l accumulates elements l, l+256, ... sequentially; xor-butterfly 16,8,4,2,1 inside each warp; the 8 warp
-// totals added in warp order) that oracle/bfr_oracle.c mirrors, so the whole loop — inlier counts, number of rounds and
-// the final transform — is bit-reproducible against the CPU oracle.  The 3x3 SVD is the same closed form as K2.
+// int(inlier_num)).  The weighted sums use a FIXED reduction tree that oracle/bfr_oracle.c mirrors, so the whole loop —
+// inlier counts, number of rounds and the final transform — is bit-reproducible against the CPU oracle:
+//     C = 1 (n <= 16384) or 8 (larger n) blocks of 256 lanes; lane l of block c accumulates elements c*256 + l, + 256 C, ...
+//     sequentially; xor-butterfly 16,8,4,2,1 inside each warp; the 8 warp totals of a block added in warp order; the C block totals
+//     added in block order.
+// One CTA of 256 threads per pair / batch element walks its C blocks one after the other; for huge pairs (BASELINE config 5: 100k
+// correspondences) post_refinement_cluster_kernel gives each block of the tree to one CTA of an 8-CTA thread-block cluster and
+// exchanges the block totals through distributed shared memory — same tree, same bits, 8 SMs instead of one.
+// The 3x3 SVD is the same closed form as K2.
 #include "bfr_common.cuh"
 #include "bfr_kernels.h"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
 
 namespace bfr {
 
 constexpr int RF_THREADS = 256;
+constexpr int RF_BIG_N = 16384;                 // more elements than this: the tree has RF_BIG_C blocks of 256 lanes
+constexpr int RF_BIG_C = 8;                     // = the (portable) cluster size of post_refinement_cluster_kernel
+
+BFR_DEVINL int rf_blocks(int n) { return n > RF_BIG_N ? RF_BIG_C : 1; }
+
+struct RfSmem {
+    float red[9][RF_THREADS / 32];
+    int redi[RF_THREADS / 32];
+    float xch[9];                               // this CTA's block total, read by the other CTAs of the cluster
+    int xchi;
+};
 
 template <int NV>
 BFR_DEVINL void block_sum(float (&v)[NV], float (*red)[RF_THREADS / 32])
@@ -48,26 +67,86 @@ BFR_DEVINL int block_sum_int(int v, int* red)
     return tot;
 }
 
+// Sum of NV per-element quantities over n elements with the fixed tree above.  acc(i, v) adds element i's terms to v.
+// CLUSTER: this CTA is block `crank` of an RF_BIG_C-CTA cluster and n > RF_BIG_N (every CTA of the cluster calls this in lock step);
+// otherwise one CTA walks the C blocks itself.  Every thread of every participating CTA returns the same totals.
+template <bool CLUSTER, int NV, typename F>
+BFR_DEVINL void tree_sum(int n, F acc, float (&tot)[NV], RfSmem& sm)
+{
+    const int C = rf_blocks(n);
+    if (CLUSTER && C > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        const int crank = (int)cluster.block_rank();
+        float v[NV];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = 0.0f;
+        for (int i = crank * RF_THREADS + threadIdx.x; i < n; i += RF_THREADS * RF_BIG_C) acc(i, v);
+        block_sum<NV>(v, sm.red);
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int k = 0; k < NV; ++k) sm.xch[k] = v[k];
+        cluster.sync();
+#pragma unroll
+        for (int k = 0; k < NV; ++k) tot[k] = 0.0f;
+        for (int c = 0; c < RF_BIG_C; ++c) {
+            const float* remote = cluster.map_shared_rank(sm.xch, c);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) tot[k] = (c == 0) ? remote[k] : __fadd_rn(tot[k], remote[k]);
+        }
+        cluster.sync();                         // everybody has read xch before it is overwritten
+    } else {
+        for (int c = 0; c < C; ++c) {
+            float v[NV];
+#pragma unroll
+            for (int k = 0; k < NV; ++k) v[k] = 0.0f;
+            for (int i = c * RF_THREADS + threadIdx.x; i < n; i += RF_THREADS * C) acc(i, v);
+            block_sum<NV>(v, sm.red);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) tot[k] = (c == 0) ? v[k] : __fadd_rn(tot[k], v[k]);
+        }
+    }
+}
+
+template <bool CLUSTER, typename F>
+BFR_DEVINL int tree_count(int n, F pred, RfSmem& sm)
+{
+    if (CLUSTER && rf_blocks(n) > 1) {
+        cg::cluster_group cluster = cg::this_cluster();
+        const int crank = (int)cluster.block_rank();
+        int cnt = 0;
+        for (int i = crank * RF_THREADS + threadIdx.x; i < n; i += RF_THREADS * RF_BIG_C) cnt += pred(i) ? 1 : 0;
+        cnt = block_sum_int(cnt, sm.redi);
+        if (threadIdx.x == 0) sm.xchi = cnt;
+        cluster.sync();
+        int tot = 0;
+        for (int c = 0; c < RF_BIG_C; ++c) tot += *cluster.map_shared_rank(&sm.xchi, c);
+        cluster.sync();
+        return tot;
+    }
+    int cnt = 0;
+    for (int i = threadIdx.x; i < n; i += RF_THREADS) cnt += pred(i) ? 1 : 0;
+    return block_sum_int(cnt, sm.redi);
+}
+
 // Weighted Kabsch over n points given by functor f(i, a[3], b[3]) -> weight.  Every thread returns the same T
 // (row-major 3x4: R | t).  Matches orc_rigid_transform_3d.
-template <typename F>
-BFR_DEVINL void weighted_kabsch_block(int n, F f, float R[9], float t[3], float (*red)[RF_THREADS / 32])
+template <bool CLUSTER, typename F>
+BFR_DEVINL void weighted_kabsch_block(int n, F f, float R[9], float t[3], RfSmem& sm)
 {
-    float s7[7] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-    for (int i = threadIdx.x; i < n; i += RF_THREADS) {
+    float s7[7];
+    tree_sum<CLUSTER, 7>(n, [&](int i, float (&v)[7]) {
         float a[3], b[3];
         const float w = f(i, a, b);
-        s7[0] = __fadd_rn(s7[0], w);
+        v[0] = __fadd_rn(v[0], w);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) { s7[1 + r] = __fmaf_rn(w, a[r], s7[1 + r]); s7[4 + r] = __fmaf_rn(w, b[r], s7[4 + r]); }
-    }
-    block_sum<7>(s7, red);
+        for (int r = 0; r < 3; ++r) { v[1 + r] = __fmaf_rn(w, a[r], v[1 + r]); v[4 + r] = __fmaf_rn(w, b[r], v[4 + r]); }
+    }, s7, sm);
     const float den = __fadd_rn(s7[0], 1e-6f);      // reference: / (sum(weights) + 1e-6), models/BUFFER.py:441-444
     float ca[3], cb[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) { ca[r] = __fdiv_rn(s7[1 + r], den); cb[r] = __fdiv_rn(s7[4 + r], den); }
-    float h9[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f };
-    for (int i = threadIdx.x; i < n; i += RF_THREADS) {
+    float h9[9];
+    tree_sum<CLUSTER, 9>(n, [&](int i, float (&v)[9]) {
         float a[3], b[3];
         const float w = f(i, a, b);
 #pragma unroll
@@ -76,10 +155,9 @@ BFR_DEVINL void weighted_kabsch_block(int n, F f, float R[9], float t[3], float 
         for (int r = 0; r < 3; ++r) {
             const float wa = __fmul_rn(w, a[r]);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) h9[3 * r + c] = __fmaf_rn(wa, b[c], h9[3 * r + c]);
+            for (int c = 0; c < 3; ++c) v[3 * r + c] = __fmaf_rn(wa, b[c], v[3 * r + c]);
         }
-    }
-    block_sum<9>(h9, red);
+    }, h9, sm);
     kabsch_rotation(h9, R);
 #pragma unroll
     for (int r = 0; r < 3; ++r)
@@ -90,17 +168,17 @@ BFR_DEVINL void weighted_kabsch_block(int n, F f, float R[9], float t[3], float 
 __global__ void __launch_bounds__(RF_THREADS) rigid_transform_kernel(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ w,
                                                                      int n, float weight_threshold, float* __restrict__ T)
 {
-    __shared__ float red[9][RF_THREADS / 32];
+    __shared__ RfSmem sm;
     const int b = blockIdx.x;
     const float* Ab = A + (size_t)b * n * 3; const float* Bb = B + (size_t)b * n * 3; const float* wb = w ? w + (size_t)b * n : nullptr;
     float R[9], t[3];
-    weighted_kabsch_block(n, [&](int i, float a[3], float q[3]) {
+    weighted_kabsch_block<false>(n, [&](int i, float a[3], float q[3]) {
         a[0] = __ldg(Ab + 3 * (size_t)i); a[1] = __ldg(Ab + 3 * (size_t)i + 1); a[2] = __ldg(Ab + 3 * (size_t)i + 2);
         q[0] = __ldg(Bb + 3 * (size_t)i); q[1] = __ldg(Bb + 3 * (size_t)i + 1); q[2] = __ldg(Bb + 3 * (size_t)i + 2);
         float wi = wb ? __ldg(wb + i) : 1.0f;
         if (wi < weight_threshold) wi = 0.0f;        // models/BUFFER.py:437
         return wi;
-    }, R, t, red);
+    }, R, t, sm);
     if (threadIdx.x == 0) {
         float* o = T + 16 * (size_t)b;
 #pragma unroll
@@ -109,15 +187,13 @@ __global__ void __launch_bounds__(RF_THREADS) rigid_transform_kernel(const float
     }
 }
 
-// post_refinement for P pairs; corr = 8-float records at corr_off[p], corr_cnt[p] of them (ALL mutual correspondences,
+// post_refinement for one pair; corr = 8-float records at corr_off[p], corr_cnt[p] of them (ALL mutual correspondences,
 // as the reference passes ss_kpts/tt_kpts, models/BUFFER.py:328).
-__global__ void __launch_bounds__(RF_THREADS) post_refinement_kernel(const float* __restrict__ T0, const float4* __restrict__ corr, const int32_t* __restrict__ corr_off,
-                                                                     const int32_t* __restrict__ corr_cnt, float thr, int max_iter,
-                                                                     float* __restrict__ Tout, int32_t* __restrict__ iters_out, int32_t* __restrict__ inliers_out)
+template <bool CLUSTER>
+BFR_DEVINL void post_refinement_pair(int p, bool writer, const float* __restrict__ T0, const float4* __restrict__ corr, const int32_t* __restrict__ corr_off,
+                                     const int32_t* __restrict__ corr_cnt, float thr, int max_iter,
+                                     float* __restrict__ Tout, int32_t* __restrict__ iters_out, int32_t* __restrict__ inliers_out, RfSmem& sm)
 {
-    __shared__ float red[9][RF_THREADS / 32];
-    __shared__ int redi[RF_THREADS / 32];
-    const int p = blockIdx.x;
     const int n = corr_cnt[p];
     const float4* c = corr + 2 * (size_t)corr_off[p];
     float R[9], t[3];
@@ -128,29 +204,27 @@ __global__ void __launch_bounds__(RF_THREADS) post_refinement_kernel(const float
     }
     int prev = 0, it = 0;
     for (; it < max_iter; ++it) {
-        int cnt = 0;
-        for (int i = threadIdx.x; i < n; i += RF_THREADS) {
+        const int cnt = tree_count<CLUSTER>(n, [&](int i) {
             const float4 a = __ldg(&c[2 * (size_t)i]), q = __ldg(&c[2 * (size_t)i + 1]);
-            cnt += (__fsqrt_rn(resid2(R, t, a.x, a.y, a.z, q.x, q.y, q.z)) < thr) ? 1 : 0;
-        }
-        cnt = block_sum_int(cnt, redi);
+            return __fsqrt_rn(resid2(R, t, a.x, a.y, a.z, q.x, q.y, q.z)) < thr;
+        }, sm);
         if (cnt == prev) break;                         // models/BUFFER.py:405-407
         prev = cnt;
         float Rn[9], tn[3];
-        weighted_kabsch_block(n, [&](int i, float a3[3], float q3[3]) {
+        weighted_kabsch_block<CLUSTER>(n, [&](int i, float a3[3], float q3[3]) {
             const float4 a = __ldg(&c[2 * (size_t)i]), q = __ldg(&c[2 * (size_t)i + 1]);
             a3[0] = a.x; a3[1] = a.y; a3[2] = a.z; q3[0] = q.x; q3[1] = q.y; q3[2] = q.z;
             const float L2 = __fsqrt_rn(resid2(R, t, a.x, a.y, a.z, q.x, q.y, q.z));
             if (!(L2 < thr)) return 0.0f;
             const float u = __fdiv_rn(L2, thr);
             return __fdiv_rn(1.0f, __fmaf_rn(u, u, 1.0f));   // models/BUFFER.py:415
-        }, Rn, tn, red);
+        }, Rn, tn, sm);
 #pragma unroll
         for (int k = 0; k < 9; ++k) R[k] = Rn[k];
 #pragma unroll
         for (int k = 0; k < 3; ++k) t[k] = tn[k];
     }
-    if (threadIdx.x == 0) {
+    if (writer && threadIdx.x == 0) {
         float* o = Tout + 16 * (size_t)p;
 #pragma unroll
         for (int r = 0; r < 3; ++r) { o[4 * r] = R[3 * r]; o[4 * r + 1] = R[3 * r + 1]; o[4 * r + 2] = R[3 * r + 2]; o[4 * r + 3] = t[r]; }
@@ -160,16 +234,50 @@ __global__ void __launch_bounds__(RF_THREADS) post_refinement_kernel(const float
     }
 }
 
+__global__ void __launch_bounds__(RF_THREADS) post_refinement_kernel(const float* __restrict__ T0, const float4* __restrict__ corr, const int32_t* __restrict__ corr_off,
+                                                                     const int32_t* __restrict__ corr_cnt, float thr, int max_iter,
+                                                                     float* __restrict__ Tout, int32_t* __restrict__ iters_out, int32_t* __restrict__ inliers_out)
+{
+    __shared__ RfSmem sm;
+    post_refinement_pair<false>((int)blockIdx.x, true, T0, corr, corr_off, corr_cnt, thr, max_iter, Tout, iters_out, inliers_out, sm);
+}
+
+// one 8-CTA cluster per pair (launched with cluster dimension RF_BIG_C): pairs with more than RF_BIG_N correspondences split the
+// reduction tree over the cluster; smaller pairs are done by every CTA on its own (identical results), CTA 0 writes
+__global__ void __launch_bounds__(RF_THREADS) post_refinement_cluster_kernel(const float* __restrict__ T0, const float4* __restrict__ corr, const int32_t* __restrict__ corr_off,
+                                                                             const int32_t* __restrict__ corr_cnt, float thr, int max_iter,
+                                                                             float* __restrict__ Tout, int32_t* __restrict__ iters_out, int32_t* __restrict__ inliers_out)
+{
+    __shared__ RfSmem sm;
+    const int p = (int)blockIdx.x / RF_BIG_C;
+    const bool big = rf_blocks(corr_cnt[p]) > 1;
+    if (!big && cg::this_cluster().block_rank() != 0) return;           // small pair: one CTA is enough (no cluster barrier is ever reached)
+    post_refinement_pair<true>(p, cg::this_cluster().block_rank() == 0, T0, corr, corr_off, corr_cnt, thr, max_iter, Tout, iters_out, inliers_out, sm);
+}
+
 cudaError_t rigid_transform_launch(const float* A, const float* B, const float* w, int bs, int n, float weight_threshold, float* T, cudaStream_t stream)
 {
     if (bs > 0) rigid_transform_kernel<<<bs, RF_THREADS, 0, stream>>>(A, B, w, n, weight_threshold, T);
     return cudaGetLastError();
 }
 
+// max_count: host-side upper bound of corr_cnt (0 = unknown).  Above RF_BIG_N the cluster kernel is used; the result does not depend
+// on the choice (the single-CTA kernel walks the same tree).
 cudaError_t post_refinement_launch(const float* T0, const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, float thr, int max_iter,
-                                   float* Tout, int32_t* iters_out, int32_t* inliers_out, cudaStream_t stream)
+                                   float* Tout, int32_t* iters_out, int32_t* inliers_out, int max_count, cudaStream_t stream)
 {
-    if (P > 0) post_refinement_kernel<<<P, RF_THREADS, 0, stream>>>(T0, reinterpret_cast<const float4*>(corr), corr_off, corr_cnt, thr, max_iter, Tout, iters_out, inliers_out);
+    if (P <= 0) return cudaSuccess;
+    if (max_count > RF_BIG_N) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)P * RF_BIG_C); cfg.blockDim = dim3(RF_THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = RF_BIG_C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const float4* c4 = reinterpret_cast<const float4*>(corr);
+        return cudaLaunchKernelEx(&cfg, post_refinement_cluster_kernel, T0, c4, corr_off, corr_cnt, thr, max_iter, Tout, iters_out, inliers_out);
+    }
+    post_refinement_kernel<<<P, RF_THREADS, 0, stream>>>(T0, reinterpret_cast<const float4*>(corr), corr_off, corr_cnt, thr, max_iter, Tout, iters_out, inliers_out);
     return cudaGetLastError();
 }
 

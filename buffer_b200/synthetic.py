@@ -85,6 +85,26 @@ def make_pairs(num_pairs, num_kpts, cfg_id=2, first_pair=0, desc_dim=32, outlier
     return PairBatch(src_des.contiguous(), tgt_des.contiguous(), src_xyz.contiguous(), tgt_xyz.contiguous(), T, perm, inlier)
 
 
+def make_lrf_votes(R_gt, inlier, azi_n=20, seed=0, device="cpu"):
+    """Synthetic inputs of the LRF vote (models/BUFFER.py:286-292) for `rows` matched keypoints: the inlier head's azimuth index
+    `ind` [rows] (integers in [0, azi_n) as float32), source frames ss_R [rows,3,3] (random rotations) and target frames tt_R with
+    tt_R Rz(ind 2 pi / azi_n) ss_R^T = R_gt for the inlier rows (random for the others).  R_gt: [rows,3,3] or [3,3]; inlier [rows] bool."""
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(7919 * seed + 13)
+    rows = inlier.shape[0]
+    f32 = dict(dtype=torch.float32, device=dev)
+    ss_R = quat_to_rot(torch.randn(rows, 4, generator=g, **f32))
+    ind = torch.randint(0, azi_n, (rows,), generator=g, device=dev).float()
+    ang = ind.double() * (2 * 3.141592653589793 / azi_n)
+    Rz = torch.zeros(rows, 3, 3, dtype=torch.float64, device=dev)
+    Rz[:, 0, 0] = torch.cos(ang); Rz[:, 0, 1] = -torch.sin(ang); Rz[:, 1, 0] = torch.sin(ang); Rz[:, 1, 1] = torch.cos(ang); Rz[:, 2, 2] = 1
+    tt_R = (R_gt.to(dev).double().expand(rows, 3, 3) @ ss_R.double() @ Rz.transpose(-1, -2)).float()
+    rnd = quat_to_rot(torch.randn(rows, 4, generator=g, **f32))
+    tt_R = torch.where(inlier.to(dev)[:, None, None], tt_R, rnd)
+    return ind.contiguous(), ss_R.contiguous(), tt_R.contiguous()
+
+
 # BASELINE.json configs (sizes are the build's, see SURVEY.md §0): keyword sets for make_pairs + RANSAC parameters
 CONFIGS = {
     1: dict(gen=dict(cfg_id=1, num_kpts=5000, outlier_ratio=0.70), num_pairs=1, hypotheses=50000, dist_th=0.10, similar_th=0.8, refine_thr=0.10),

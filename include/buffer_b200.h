@@ -9,8 +9,12 @@
  * Conventions
  *  - extern "C", plain pointers and sizes; no torch / C++ types.  `stream` is a cudaStream_t passed as void*.
  *  - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory including the
- *    workspace (`ws`, size from the matching *_workspace_bytes); the library never allocates device memory, keeps no
- *    per-call global state, and every call is asynchronous on `stream` (no host sync inside) unless stated.
+ *    workspace (`ws`, size from the matching *_workspace_bytes); the library never allocates device memory and every
+ *    call is asynchronous on `stream` (no host sync inside) unless stated.  State kept by the library: the per-THREAD
+ *    tuning knob of bfr_config_set / the per-thread debug events (each host thread sees only its own), and one
+ *    "shared-memory opt-in done" bit per kernel and device ordinal (idempotent) - calls from several host threads
+ *    and on several devices of one process are safe.  Launches go to the CURRENT device of the calling thread: make
+ *    the device that owns the buffers current before calling.
  *  - Batches are "varlen": pair p owns rows [off[p], off[p+1]) of the concatenated arrays; offsets are int32 DEVICE
  *    arrays of P+1 entries; max_M / max_N are host-side upper bounds of the per-pair row counts (grid sizing).
  *  - Row-major float32 everywhere.  Descriptor / keypoint base pointers must be 16-byte aligned (TMA bulk copies).
@@ -39,9 +43,9 @@ extern "C" {
 int bfr_version(void);
 const char* bfr_error_string(int code);
 
-/* Process-wide tuning knobs.  BFR_CFG_K1_ALGO selects the mutual-NN implementation: 0 = FP32 FFMA2 kernel (every product
- * in FP32), 1 = tensor-core (tcgen05, f16 operands) filter followed by an exact FP32 re-check of the near-best candidates.  Both
- * produce bit-identical outputs. */
+/* Tuning knobs of the CALLING THREAD (thread-local; default 1 in every thread).  BFR_CFG_K1_ALGO selects the mutual-NN
+ * implementation: 0 = FP32 FFMA2 kernel (every product in FP32), 1 = tensor-core (tcgen05, f16 operands) filter followed by an
+ * exact FP32 re-check of the near-best candidates.  Both produce bit-identical outputs. */
 #define BFR_CFG_K1_ALGO 1
 int bfr_config_set(int key, int value);
 int bfr_config_get(int key);
@@ -53,13 +57,32 @@ int bfr_config_get(int key);
  * p, ascending in s, written at s_mids[src_off[p] ...] with n_mutual[p] entries (models/BUFFER.py:356-357); corr_xyz =
  * the matched keypoints gathered into correspondence records at the same offsets (models/BUFFER.py:284,287; needs
  * src_xyz/tgt_xyz [rows][3]).  col_splits >= 1 splits the target rows of each pair over that many CTAs (use > 1 when P
- * is too small to fill 148 SMs).  total_M / total_N = rows of the concatenated descriptor arrays (TMA tensor-map bounds). */
+ * is too small to fill 148 SMs).  total_M / total_N = rows of the concatenated descriptor arrays (TMA tensor-map bounds).
+ * max_M / max_N must be >= every pair's row count: a larger pair is truncated to the bound (never read out of its workspace slice). */
 size_t bfr_mutual_nn_workspace_bytes(int P, int max_M, int max_N);
 int bfr_mutual_matching_batched(const float* src_des, const float* tgt_des, const int32_t* src_off, const int32_t* tgt_off,
                                 int P, int max_M, int max_N, int total_M, int total_N, int D, int col_splits,
                                 int64_t* nn_s, int64_t* nn_t, float* dist_s, float* dist_t,
                                 const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr_xyz,
                                 void* ws, size_t ws_bytes, void* stream);
+
+/* The same in phases, for ONE HUGE PAIR whose rows are split over several GPUs (BASELINE config 5: 100k x 100k keypoints):
+ *   bfr_mutual_nn_partial  half norms / operand copies for all rows, then the fused distance + arg-max kernel on row-block
+ *                          partition `part` of `nparts` (source rows of the src->tgt direction and target rows of the tgt->src
+ *                          direction are both partitioned); the packed bests (key << 32 | ~index, 0 = untouched) stay in `ws`;
+ *   bfr_mutual_nn_packed   the contiguous uint64 region of `ws` holding them (row bests then column bests, `count` entries):
+ *                          the caller max-reduces it across ranks as UNSIGNED 64-bit (NCCL all-reduce over NVLink; with a signed
+ *                          reduction flip bit 63 before and after);
+ *   bfr_mutual_select      decode + mutual check + ordered compaction (+ gather) from the reduced bests - same outputs as
+ *                          bfr_mutual_matching_batched, which is exactly partial(0, 1) followed by select. */
+int bfr_mutual_nn_partial(const float* src_des, const float* tgt_des, const int32_t* src_off, const int32_t* tgt_off,
+                          int P, int max_M, int max_N, int total_M, int total_N, int D, int col_splits, int part, int nparts,
+                          void* ws, size_t ws_bytes, void* stream);
+int bfr_mutual_nn_packed(void* ws, size_t ws_bytes, int P, int max_M, int max_N, uint64_t** packed, size_t* count);
+int bfr_mutual_select(const int32_t* src_off, const int32_t* tgt_off, int P, int max_M, int max_N,
+                      int64_t* nn_s, int64_t* nn_t, float* dist_s, float* dist_t,
+                      const float* src_xyz, const float* tgt_xyz, int64_t* s_mids, int64_t* t_mids, int32_t* n_mutual, float* corr_xyz,
+                      void* ws, size_t ws_bytes, void* stream);
 
 /* Gather explicit index pairs into correspondence records: the (pcd0, pcd1, corr) arguments of the Open3D call at
  * models/BUFFER.py:314-316.  s_ids/t_ids: int64 [K]. */
@@ -73,10 +96,15 @@ int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s
  * (inlier count << 32) | (0xFFFFFFFF - h): the caller zeroes best_packed before the first call and may split the
  * hypothesis range over several calls, streams or GPUs (all-reduce MAX) before finalising.  corr_cnt[p] < 3 leaves 0.
  * valid_count (optional, [P] int32, zeroed by the caller) accumulates how many hypotheses passed every checker and were
- * scored — the H_valid of the 28*H_valid*C scoring-work model. */
+ * scored — the H_valid of the 28*H_valid*C scoring-work model.
+ * confidence: RANSACConvergenceCriteria(iter_n, confidence) of models/BUFFER.py:323-324.  >= 1 (KITTI/config.py:65) or <= 0:
+ * every hypothesis of the range is evaluated.  In (0, 1) (ThreeDMatch/config.py:65 = 0.999): Open3D's rule, evaluated as by ONE
+ * sequential thread - iteration i (= h - h_begin) only runs while i < min(h_end - h_begin, ceil(log(1 - confidence) /
+ * log(1 - (best_count / K)^3))) of the best hypothesis before it; the result is the best of exactly those iterations.  The rule
+ * is sequential in h, so one call must cover the pair's whole range (no split over calls / GPUs) and `splits` is ignored. */
 int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
                        uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
-                       float dist_th, float similar_th, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream);
+                       float dist_th, float similar_th, float confidence, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream);
 /* Decode best_packed and regenerate the winning minimal-sample fit: T [P][16] row-major 4x4 (result.transformation,
  * models/BUFFER.py:326), inlier count and hypothesis index (-1 if none; T = identity). */
 int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
@@ -86,31 +114,56 @@ int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, 
 /* ---- a3 / a4: per-correspondence LRF hypotheses and their scoring --------------------------------------------------
  * bfr_lrf_hypotheses replaces models/BUFFER.py:294-301: R = tt_R Rz(angle) ss_R^T, t = tt_kpts - R ss_kpts; cs[i] =
  * {cos(angle_i), sin(angle_i)} is supplied by the caller.  bfr_score_hypotheses replaces models/BUFFER.py:303-311:
- * counts[h] = #{c : |R_h s_c + t_h - q_c| < thr_c}; best_idx = first maximum (torch.argmax); mask = inliers of the
- * best.  thr: [C] per-correspondence thresholds or NULL (then thr_scalar). */
+ * counts[h] = #{c : sqrt(|R_h s_c + t_h - q_c|^2) < thr_c} (the reference's test on the rooted distance, :305-308); best_idx =
+ * first maximum (torch.argmax); mask = inliers of the best.  thr: [C] per-correspondence thresholds or NULL (then thr_scalar). */
 int bfr_lrf_hypotheses(const float* cs, const float* ss_R, const float* tt_R, const float* ss_kpts, const float* tt_kpts, int A,
                        float* R_out, float* t_out, void* stream);
 size_t bfr_score_workspace_bytes(int C);
 int bfr_score_hypotheses(const float* R, const float* t, int H, const float* src, const float* tgt, int C, const float* thr, float thr_scalar,
                          int32_t* counts, uint64_t* best_packed, int64_t* best_idx, uint8_t* mask, void* ws, size_t ws_bytes, void* stream);
 
+/* The two blocks fused and batched over pairs - the LRF vote, models/BUFFER.py:294-311 - with everything on the device:
+ * corr_xyz = the records of ALL mutual matches of each pair (K1's corr_xyz output; the 4th float of every record is overwritten
+ * with the vote threshold), ind [rows] = the inlier head's azimuth index per match (:291-292), ss_R / tt_R [rows][9] = the matched
+ * local reference frames (s_R[s_mids], t_R[t_mids], :286,:289), all row-aligned with corr_xyz.  Per pair: proposal c is
+ * R = tt_R[c] Rz(ind_c 2 pi / azi_n + 1e-6) ss_R[c]^T, t = q_c - R s_c (cos / sin by a pinned polynomial, mirrored in the oracle; R, t
+ * only exist in registers); inlier_num (optional, [rows]) = inliers of every proposal under thr_c = |s_c| pi / azi_n inlier_th;
+ * best_ind [P] (optional) = first maximum; sub_corr [rows][8] / sub_cnt [P] = the inliers of the winner compacted in ascending
+ * order at the pair's offset - the `corr` of the Open3D call (:311-316); inlier_ind (optional, [rows]) their indices.
+ * bfr_pose_from_votes_batched = that vote -> RANSAC on the voted subset (:313-326) -> post_refinement on ALL matches (:327-329),
+ * one call, no host sync: the reference's stage flow after the inlier head. */
+size_t bfr_vote_workspace_bytes(int P, int total_rows);
+int bfr_lrf_vote_batched(float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P, int max_count, int total_rows,
+                         const float* ind, const float* ss_R, const float* tt_R, float azi_n, float inlier_th,
+                         int32_t* inlier_num, int64_t* best_ind, float* sub_corr, int32_t* sub_cnt, int64_t* inlier_ind,
+                         void* ws, size_t ws_bytes, void* stream);
+int bfr_pose_from_votes_batched(float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P, int max_count, int total_rows,
+                                const float* ind, const float* ss_R, const float* tt_R, float azi_n, float inlier_th,
+                                int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th, float confidence,
+                                float refine_thr, int refine_iters, int ransac_splits,
+                                float* T_out, int32_t* n_vote_inliers, int32_t* n_inliers, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- K4: weighted Kabsch and post-refinement ------------------------------------------------------------------------
  * bfr_rigid_transform_3d replaces rigid_transform_3d (models/BUFFER.py:424-464): A, B [bs][n][3], w [bs][n] or NULL,
  * T [bs][16].  bfr_post_refinement_batched replaces buffer.post_refinement (models/BUFFER.py:382-418) for P pairs:
- * T0/T_out [P][16]; thr = 0.10 (3DMatch/3DLoMatch/ETH) or 1.2 (KITTI), max_iter = 20 in the reference. */
+ * T0/T_out [P][16]; thr = 0.10 (3DMatch/3DLoMatch/ETH) or 1.2 (KITTI), max_iter = 20 in the reference.  max_count = host-side
+ * upper bound of corr_cnt (0 = unknown): above 16384 every pair gets an 8-CTA thread-block cluster instead of one CTA (the result
+ * does not depend on it: both kernels walk the same fixed reduction tree). */
 int bfr_rigid_transform_3d(const float* A, const float* B, const float* w, int bs, int n, float weight_threshold, float* T, void* stream);
 int bfr_post_refinement_batched(const float* T0, const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
-                                float thr, int max_iter, float* T_out, int32_t* iters, int32_t* inliers, void* stream);
+                                float thr, int max_iter, int max_count, float* T_out, int32_t* iters, int32_t* inliers, void* stream);
 
 /* ---- whole back end: descriptors + keypoints -> pose, one call, no host sync -----------------------------------------
  * The test branch of buffer.forward after the descriptors exist, without the learned inlier head:
  * mutual_matching (:283) -> gather (:284-287) -> RANSAC on all mutual matches (:313-326) -> post_refinement (:327-329).
- * refine_iters = 0 skips refinement (KITTI config, pose_refine=False).  total_M/total_N = rows of the concatenated arrays. */
+ * refine_iters = 0 skips refinement (KITTI config, pose_refine=False).  total_M/total_N = rows of the concatenated arrays.
+ * confidence: see bfr_ransac_batched (1.0 = evaluate all `hypotheses`).  With the learned inlier head in the loop use
+ * bfr_mutual_matching_batched -> (head) -> bfr_pose_from_votes_batched instead. */
 size_t bfr_register_workspace_bytes(int P, int max_M, int max_N, int total_M, int total_N);
 int bfr_register_batched(const float* src_des, const float* src_xyz, const int32_t* src_off,
                          const float* tgt_des, const float* tgt_xyz, const int32_t* tgt_off,
                          int P, int max_M, int max_N, int total_M, int total_N, int D,
-                         int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th,
+                         int hypotheses, uint64_t seed, uint32_t pair_id_base, float dist_th, float similar_th, float confidence,
                          float refine_thr, int refine_iters, int ransac_splits,
                          float* T_out, int32_t* n_mutual, int32_t* n_inliers, void* ws, size_t ws_bytes, void* stream);
 
@@ -121,7 +174,7 @@ int bfr_register_batched(const float* src_des, const float* src_xyz, const int32
 size_t bfr_register_host_workspace_bytes(int P, int M, int N, int D);
 int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_host, const float* tgt_des_host, const float* tgt_xyz_host,
                               int P, int M, int N, int D, int hypotheses, uint64_t seed, uint32_t pair_id_base,
-                              float dist_th, float similar_th, float refine_thr, int refine_iters, int ransac_splits,
+                              float dist_th, float similar_th, float confidence, float refine_thr, int refine_iters, int ransac_splits,
                               float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- "next" rows ------------------------------------------------------------------------------------

@@ -221,7 +221,48 @@ def gen_evaluation():
     print("evaluation.npz: %d gt pairs, %d estimates, precision %.3f recall %.3f, DGR recall %.3f" % (len(pairs), len(est_pairs), precision, recall, states[:, 0].mean()))
 
 
+def gen_config1():
+    """BASELINE config 1 at full size: ONE 3DMatch-sized pair (5 000 x 5 000 keypoints, 32-d, 70 % outliers) through the reference's own
+    functions: buffer.mutual_matching, the inline vote block (:294-311), the Open3D-semantics loop on the reference's Kabsch for the first
+    5 000 hypotheses of the shared Philox stream, buffer.post_refinement on all matches.  The inputs are NOT stored (2.6 MB): they are
+    regenerated from the seed (buffer_b200.synthetic, CPU generator) and checked against the stored checksums."""
+    c = S.CONFIGS[1]
+    b = S.make_pairs(1, first_pair=0, **c["gen"])
+    N = c["gen"]["num_kpts"]
+    src_des, tgt_des = b.src_des[0].numpy(), b.tgt_des[0].numpy()
+    src_xyz, tgt_xyz = b.src_xyz[0].numpy(), b.tgt_xyz[0].numpy()
+    s_mids, t_mids = RI.mutual_matching(src_des, tgt_des)
+    ss, tt = src_xyz[s_mids], tgt_xyz[t_mids]
+    K = len(s_mids); H = 5000; seed = 0xB0FFE7; pair_id = 0
+    samples = np.stack([O.sample3(seed, pair_id, h, K) for h in range(H)]).astype(np.int64)
+    corr = np.stack([np.arange(K), np.arange(K)], 1)
+    T_best, best_cnt, best_h, counts = RI.ransac_open3d_semantics(ss, tt, corr, c["dist_th"], c["similar_th"], samples)
+    T_ref = RI.post_refinement(T_best, ss, tt, "3DMatch")
+    # the vote block on all K matches
+    inl = b.inlier[0].numpy()[s_mids]
+    ind, ss_R, tt_R = S.make_lrf_votes(b.T_gt[0, :3, :3], torch.from_numpy(inl), azi_n=20, seed=1)
+    R_h, t_h = RI.lrf_hypotheses(ind.numpy(), ss_R.numpy(), tt_R.numpy(), ss, tt, azi_n=20)
+    inlier_num, best_ind, inlier_ind, thr = RI.score_hypotheses(R_h, t_h, ss, tt, azi_n=20, inlier_th=1 / 3)
+    # reference flow :313-329 on the voted subset
+    sub = np.stack([inlier_ind, inlier_ind], 1)
+    samples2 = np.stack([O.sample3(seed, pair_id, h, len(sub)) for h in range(H)]).astype(np.int64)
+    T_best2, best_cnt2, best_h2, counts2 = RI.ransac_open3d_semantics(ss, tt, sub, c["dist_th"], c["similar_th"], samples2)
+    T_ref2 = RI.post_refinement(T_best2, ss, tt, "3DMatch")
+    chk = np.array([np.float64(x.astype(np.float64).sum()) for x in (src_des, tgt_des, src_xyz, tgt_xyz, ss_R.numpy(), tt_R.numpy(), ind.numpy())])
+    np.savez_compressed(os.path.join(OUT, "config1.npz"), checksums=chk, N=np.int64(N), s_mids=s_mids.astype(np.int16), t_mids=t_mids.astype(np.int16),
+                        H=np.int64(H), seed=np.uint64(seed), pair_id=np.uint32(pair_id), dist_th=np.float32(c["dist_th"]), similar_th=np.float32(c["similar_th"]),
+                        counts=counts.astype(np.int16), best_h=np.int64(best_h), best_count=np.int64(best_cnt), T_best=T_best, T_refined=T_ref, T_gt=b.T_gt[0].numpy(),
+                        vote_inlier_num=inlier_num.astype(np.int16), vote_best_ind=np.int64(best_ind), vote_inlier_ind=inlier_ind.astype(np.int16),
+                        sub_counts=counts2.astype(np.int16), sub_best_h=np.int64(best_h2), sub_best_count=np.int64(best_cnt2), sub_T_best=T_best2, sub_T_refined=T_ref2)
+    print("config1.npz: %d mutual matches, RANSAC winner h=%d with %d inliers (%d valid of %d); vote winner %d with %d inliers; subset RANSAC h=%d with %d inliers; %d bytes"
+          % (K, best_h, best_cnt, int((counts >= 0).sum()), H, best_ind, len(inlier_ind), best_h2, best_cnt2, os.path.getsize(os.path.join(OUT, "config1.npz"))))
+
+
 if __name__ == "__main__":
+    if "--config1" in sys.argv:             # `--config1`: only (re)generate config1.npz
+        gen_config1()
+        sys.exit(0)
     if "--evaluation" not in sys.argv:      # `--evaluation`: only (re)generate evaluation.npz
         main()
+        gen_config1()
     gen_evaluation()

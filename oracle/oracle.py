@@ -35,6 +35,12 @@ def lib():
         _lib.orc_hypothesis.restype = C.c_int
         _lib.orc_count_inliers.restype = C.c_int32
         _lib.orc_kabsch_rotation.restype = C.c_int
+        _lib.orc_ransac_confidence.restype = C.c_uint64
+        _lib.orc_sqrt_threshold.restype = C.c_float
+        _lib.orc_vote_threshold.restype = C.c_float
+        _lib.orc_det_log.restype = C.c_double
+        _lib.orc_ransac_exit_bound.restype = C.c_uint32
+        _lib.orc_lrf_vote.restype = C.c_int32
     return _lib
 
 
@@ -129,6 +135,55 @@ def ransac(corr, seed, pair_id, H, dist_th, similar_th, h_begin=0, h_end=None, w
     return (int(best), counts) if want_counts else int(best)
 
 
+def ransac_confidence(corr, seed, pair_id, H, dist_th, similar_th, confidence, h_begin=0):
+    """Open3D's confidence early exit replayed sequentially (models/BUFFER.py:323-324) -> (packed best, iterations run)"""
+    corr = _f32(corr); it = C.c_uint32(0)
+    best = lib().orc_ransac_confidence(_p(corr), C.c_uint32(corr.shape[0]), C.c_uint64(seed), C.c_uint32(pair_id), C.c_uint32(h_begin),
+                                       C.c_uint32(h_begin + H), C.c_float(dist_th), C.c_float(similar_th), C.c_float(confidence), C.byref(it))
+    return int(best), int(it.value)
+
+
+def sqrt_threshold(thr):
+    return float(lib().orc_sqrt_threshold(C.c_float(thr)))
+
+
+def det_sincos(a):
+    sn = C.c_float(0); cs = C.c_float(0)
+    lib().orc_det_sincos(C.c_float(a), C.byref(sn), C.byref(cs))
+    return sn.value, cs.value
+
+
+def det_log(v):
+    return float(lib().orc_det_log(C.c_double(v)))
+
+
+def ransac_exit_bound(count, K, confidence, max_iter):
+    return int(lib().orc_ransac_exit_bound(C.c_uint32(count), C.c_uint32(K), C.c_double(det_log(1.0 - float(np.float32(confidence)))), C.c_uint32(max_iter)))
+
+
+def lrf_vote(corr, ind, ss_R, tt_R, azi_n=20.0, inlier_th=1.0 / 3.0):
+    """models/BUFFER.py:294-311 for one pair -> inlier_num [A] int32, best_ind, inlier_ind [K] int64"""
+    corr = _f32(corr); ind = _f32(ind); ss_R = _f32(ss_R).reshape(-1, 9); tt_R = _f32(tt_R).reshape(-1, 9)
+    A = corr.shape[0]
+    counts = np.zeros(A, np.int32); best = C.c_int64(-1); sel = np.zeros(max(A, 1), np.int64)
+    k = lib().orc_lrf_vote(_p(corr), C.c_int(A), _p(ind), _p(ss_R), _p(tt_R), C.c_float(azi_n), C.c_float(inlier_th), _p(counts), C.byref(best), _p(sel))
+    return counts, best.value, sel[:k].copy()
+
+
+def pose_from_votes_batched(corr, corr_off, corr_cnt, ind, ss_R, tt_R, H, seed, pair_id_base, dist_th, similar_th, confidence=1.0,
+                            refine_thr=0.1, refine_iters=20, azi_n=20.0, inlier_th=1.0 / 3.0):
+    """vote -> RANSAC on the voted subset -> refinement on all matches (models/BUFFER.py:291-329), OpenMP over pairs
+    -> T [P,4,4], n_vote_inliers [P], n_inliers [P]"""
+    corr = _f32(corr); ind = _f32(ind); ss_R = _f32(ss_R).reshape(-1, 9); tt_R = _f32(tt_R).reshape(-1, 9)
+    corr_off = np.ascontiguousarray(corr_off, np.int32); corr_cnt = np.ascontiguousarray(corr_cnt, np.int32)
+    P = len(corr_cnt)
+    T = np.zeros((P, 16), np.float32); nv = np.zeros(P, np.int32); ni = np.zeros(P, np.int32)
+    lib().orc_pose_from_votes_batched(_p(corr), _p(corr_off), _p(corr_cnt), C.c_int(P), _p(ind), _p(ss_R), _p(tt_R), C.c_float(azi_n), C.c_float(inlier_th),
+                                      C.c_int(H), C.c_uint64(seed), C.c_uint32(pair_id_base), C.c_float(dist_th), C.c_float(similar_th), C.c_float(confidence),
+                                      C.c_float(refine_thr), C.c_int(refine_iters), _p(T), _p(nv), _p(ni))
+    return T.reshape(P, 4, 4), nv, ni
+
+
 def ransac_finalize(corr, seed, pair_id, best, dist_th, similar_th):
     """-> T [4,4] float32, inlier count, best hypothesis index (-1 if none)"""
     corr = _f32(corr); T = np.zeros(16, np.float32); cnt = C.c_int32(0); bh = C.c_int64(0)
@@ -203,7 +258,7 @@ def svd3(x):
 
 
 def register_batched(src_des, src_xyz, src_off, tgt_des, tgt_xyz, tgt_off, H, seed, pair_id_base, dist_th, similar_th,
-                     refine_thr, refine_iters=20):
+                     refine_thr, refine_iters=20, confidence=1.0):
     """whole back end on the CPU for a batch of pairs (OpenMP over pairs) -> T [P,4,4], n_mutual [P], n_inliers [P]"""
     src_des = _f32(src_des); tgt_des = _f32(tgt_des); src_xyz = _f32(src_xyz); tgt_xyz = _f32(tgt_xyz)
     src_off = np.ascontiguousarray(src_off, np.int32); tgt_off = np.ascontiguousarray(tgt_off, np.int32)
@@ -211,6 +266,6 @@ def register_batched(src_des, src_xyz, src_off, tgt_des, tgt_xyz, tgt_off, H, se
     T = np.zeros((P, 16), np.float32); nm = np.zeros(P, np.int32); ni = np.zeros(P, np.int32)
     lib().orc_register_batched(_p(src_des), _p(src_xyz), _p(src_off), _p(tgt_des), _p(tgt_xyz), _p(tgt_off), C.c_int(P),
                                C.c_int(src_des.shape[1]), C.c_int(H), C.c_uint64(seed), C.c_uint32(pair_id_base),
-                               C.c_float(dist_th), C.c_float(similar_th), C.c_float(refine_thr), C.c_int(refine_iters),
+                               C.c_float(dist_th), C.c_float(similar_th), C.c_float(confidence), C.c_float(refine_thr), C.c_int(refine_iters),
                                _p(T), _p(nm), _p(ni))
     return T.reshape(P, 4, 4), nm, ni

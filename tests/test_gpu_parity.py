@@ -163,7 +163,8 @@ def test_open3d_style_call(oracle, backend):
     res = backend.registration_ransac_based_on_correspondence(b.src_xyz[0].to(DEV), b.tgt_xyz[0].to(DEV), corr_idx, 0.1, 0.8, iter_n=5000,
                                                               confidence=0.999, seed=3, pair_id=1)
     corr = oracle.gather_corr(b.src_xyz[0].numpy(), b.tgt_xyz[0].numpy(), s[keep], t[keep])
-    best = oracle.ransac(corr, 3, 1, 5000, 0.1, 0.8)
+    best, iters = oracle.ransac_confidence(corr, 3, 1, 5000, 0.1, 0.8, 0.999)      # the reference's 3DMatch criteria (config.py:65)
+    assert iters < 5000
     T_o, cnt_o, _ = oracle.ransac_finalize(corr, 3, 1, best, 0.1, 0.8)
     assert res.transformation.dtype == np.float64 and res.transformation.shape == (4, 4)
     assert np.array_equal(res.transformation.astype(np.float32), T_o) and res.inlier_count == cnt_o
@@ -283,15 +284,153 @@ def test_furthest_point_sample_bit_exact(oracle, backend):
     assert float(d) < 0.45
 
 
-def test_lrf_vote_matches_separate_calls(backend):
-    A = 300
-    g = torch.Generator().manual_seed(4)
-    ss_R = S.quat_to_rot(torch.randn(A, 4, generator=g)).to(DEV); tt_R = S.quat_to_rot(torch.randn(A, 4, generator=g)).to(DEV)
-    ss = (torch.rand(A, 3, generator=g) * 3).to(DEV); tt = (torch.rand(A, 3, generator=g) * 3).to(DEV); ind = (torch.rand(A, generator=g) * 20).to(DEV)
-    R, t, counts, best, mask = backend.lrf_vote(ind, ss_R, tt_R, ss, tt)
-    R2, t2 = backend.lrf_hypotheses(ind, ss_R, tt_R, ss, tt)
-    c2, b2, m2 = backend.score_hypotheses(R2, t2, ss, tt, backend.inlier_threshold(ss))
-    assert torch.equal(R, R2) and torch.equal(counts, c2) and torch.equal(best, b2) and torch.equal(mask, m2)
+def _vote_batch(P, N, cfg_id, rho=0.7):
+    """P pairs with LRF-vote inputs: records of all mutual matches (from the oracle), ind / ss_R / tt_R row-aligned"""
+    from oracle import oracle as O
+    b = _pairs(P, N, cfg_id=cfg_id, outlier_ratio=rho)
+    corr, ind, ssR, ttR, cnt = [], [], [], [], []
+    for p in range(P):
+        s, t = O.mutual_matching(b.src_des[p].numpy(), b.tgt_des[p].numpy())
+        c = O.gather_corr(b.src_xyz[p].numpy(), b.tgt_xyz[p].numpy(), s, t)
+        i_, sr, tr = S.make_lrf_votes(b.T_gt[p, :3, :3], b.inlier[p][torch.from_numpy(s)], seed=100 * cfg_id + p)
+        corr.append(c); ind.append(i_.numpy()); ssR.append(sr.numpy()); ttR.append(tr.numpy()); cnt.append(len(s))
+    off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    return b, np.concatenate(corr), np.concatenate(ind), np.concatenate(ssR), np.concatenate(ttR), off, np.asarray(cnt, np.int32)
+
+
+def test_lrf_vote_batched_bit_exact(oracle, backend):
+    """the fused LRF vote (models/BUFFER.py:294-311): counts of every proposal, the winner and the compacted inlier subset"""
+    b, corr, ind, ssR, ttR, off, cnt = _vote_batch(3, 900, 23)
+    cnt[2] = 2; ragged = np.concatenate([np.arange(off[p], off[p] + cnt[p]) for p in range(3)])      # a degenerate pair too
+    d = lambda a: torch.from_numpy(a).to(DEV)
+    r = backend.lrf_vote_batched(d(corr), d(off), d(cnt), d(ind), d(ssR), d(ttR), int(cnt.max()))
+    torch.cuda.synchronize()
+    for p in range(3):
+        sl = slice(off[p], off[p] + cnt[p])
+        c_o, b_o, sel_o = oracle.lrf_vote(corr[sl], ind[sl], ssR[sl], ttR[sl])
+        k = int(r["sub_cnt"][p].item())
+        assert np.array_equal(r["inlier_num"][sl].cpu().numpy(), c_o) and int(r["best_ind"][p].item()) == b_o
+        assert k == len(sel_o) and np.array_equal(r["inlier_ind"][off[p]:off[p] + k].cpu().numpy(), sel_o)
+        sub = r["sub_corr"][off[p]:off[p] + k].cpu().numpy()
+        assert np.array_equal(sub[:, [0, 1, 2, 4, 5, 6]], corr[sl][sel_o][:, [0, 1, 2, 4, 5, 6]])
+    assert int(r["sub_cnt"][0].item()) > 200
+
+
+def test_pose_from_votes_matches_oracle(oracle, backend):
+    """the reference's stage flow in one call (vote -> RANSAC on the voted subset -> refinement on ALL matches), with and without
+    Open3D's confidence early exit"""
+    b, corr, ind, ssR, ttR, off, cnt = _vote_batch(4, 1100, 29)
+    d = lambda a: torch.from_numpy(a).to(DEV)
+    for conf in (1.0, 0.999):
+        To, nv_o, ni_o = oracle.pose_from_votes_batched(corr, off[:-1], cnt, ind, ssR, ttR, 6000, 77, 10, 0.1, 0.8, conf, 0.1, 20)
+        T, nv, ni = backend.pose_from_votes_batched(d(corr.copy()), d(off), d(cnt), d(ind), d(ssR), d(ttR), int(cnt.max()), hypotheses=6000, seed=77,
+                                                    pair_id_base=10, confidence=conf)
+        assert np.array_equal(nv.cpu().numpy(), nv_o) and np.array_equal(ni.cpu().numpy(), ni_o)
+        assert np.array_equal(T.cpu().numpy(), To)
+        recall, rte, rre = S.registration_recall(T.cpu(), b.T_gt)
+        assert recall == 1.0 and float(rte.max()) < 0.01
+
+
+@pytest.mark.parametrize("N,H,rho,conf", [(700, 5000, 0.7, 0.999), (2500, 20000, 0.7, 0.99), (1500, 30000, 0.9, 0.999), (6000, 20000, 0.8, 0.999)])
+def test_ransac_confidence_bit_exact(oracle, backend, N, H, rho, conf):
+    """Open3D's RANSACConvergenceCriteria(iter_n, confidence) (models/BUFFER.py:323-324): the GPU replays the sequential rule exactly"""
+    b = _pairs(3, N, cfg_id=37, outlier_ratio=rho)
+    corrs, cnts = [], []
+    for p in range(3):
+        s, t = oracle.mutual_matching(b.src_des[p].numpy(), b.tgt_des[p].numpy())
+        corrs.append(oracle.gather_corr(b.src_xyz[p].numpy(), b.tgt_xyz[p].numpy(), s, t)); cnts.append(len(s))
+    off = np.concatenate([[0], np.cumsum(cnts)]).astype(np.int32)
+    cd = torch.from_numpy(np.concatenate(corrs)).to(DEV)
+    od = torch.from_numpy(off).to(DEV); cn = torch.tensor(cnts, dtype=torch.int32, device=DEV)
+    nv = torch.zeros(3, dtype=torch.int32, device=DEV)
+    bp = backend.ransac_batched(cd, od, cn, H, 0.1, 0.8, seed=91, pair_id_base=5, h_begin=100, h_end=100 + H, confidence=conf, valid_count=nv)
+    full = backend.ransac_batched(cd, od, cn, H, 0.1, 0.8, seed=91, pair_id_base=5, h_begin=100, h_end=100 + H)
+    for p in range(3):
+        best_o, iters = oracle.ransac_confidence(corrs[p], 91, 5 + p, H, 0.1, 0.8, conf, h_begin=100)
+        assert int(bp[p].item()) == best_o, (p, iters)
+        assert iters < H and int(nv[p].item()) <= int((oracle.ransac(corrs[p], 91, 5 + p, H, 0.1, 0.8, 100, 100 + H, want_counts=True)[1] >= 0).sum())
+        assert int(full[p].item()) >= best_o                          # the full run can only be at least as good
+
+
+def test_mutual_nn_row_split_equals_whole(oracle, backend, algo):
+    """K1 in phases (the multi-GPU row split of one huge pair): partitions run one after the other into separate workspaces, the packed
+    bests merged by an unsigned 64-bit max (what the all-reduce does), then select == the one-call path, bit for bit"""
+    g = torch.Generator().manual_seed(19)
+    nrm = lambda x: torch.nn.functional.normalize(x, dim=-1)
+    M, N = 3300, 2900
+    src = nrm(torch.randn(M, 32, generator=g)); tgt = nrm(torch.randn(N, 32, generator=g))
+    tgt[:1500] = nrm(src[:1500] + 0.05 * torch.randn(1500, 32, generator=g)); tgt[7] = tgt[3]
+    sx = torch.randn(M, 3, generator=g); tx = torch.randn(N, 3, generator=g)
+    so = torch.tensor([0, M], dtype=torch.int32, device=DEV); to = torch.tensor([0, N], dtype=torch.int32, device=DEV)
+    whole = backend.mutual_matching_batched(src.to(DEV), tgt.to(DEV), so, to, M, N, sx.to(DEV), tx.to(DEV))
+    for nparts in (2, 3, 8):
+        merged = None
+        for part in range(nparts):
+            sp = backend.MutualNNSplit(src.to(DEV), tgt.to(DEV), so, to, M, N)
+            pk = sp.partial(part, nparts).clone() ^ -0x8000000000000000      # unsigned order -> signed order
+            merged = pk if merged is None else torch.maximum(merged, pk)
+        sp.packed.copy_(merged ^ -0x8000000000000000)
+        out = sp.select(sx.to(DEV), tx.to(DEV))
+        n = int(out["n_mutual"].item())
+        assert n == int(whole["n_mutual"].item())
+        for key in ("nn_s", "nn_t"):
+            assert torch.equal(out[key], whole[key]), (nparts, key)
+        assert torch.equal(out["s_mids"][:n], whole["s_mids"][:n]) and torch.equal(out["corr"][:n], whole["corr"][:n])
+    nn_s, nn_t = oracle.mutual_nn(src.numpy(), tgt.numpy())
+    assert np.array_equal(whole["nn_s"].cpu().numpy(), nn_s) and np.array_equal(whole["nn_t"].cpu().numpy(), nn_t)
+
+
+def test_post_refinement_big_pair_cluster_bit_exact(oracle, backend):
+    """more than 16384 correspondences: the 8-block reduction tree, run by an 8-CTA cluster (max_count given) or by one CTA - same bits"""
+    n = 40000
+    g = torch.Generator().manual_seed(6)
+    src = torch.rand(n, 3, generator=g) * 3; Rg = S.quat_to_rot(torch.randn(1, 4, generator=g))[0]; tg = torch.rand(3, generator=g)
+    tgt = src @ Rg.T + tg + 0.01 * torch.randn(n, 3, generator=g)
+    out = torch.rand(n, generator=g) < 0.6; tgt[out] = torch.rand(int(out.sum()), 3, generator=g) * 3
+    corr = np.zeros((n, 8), np.float32); corr[:, :3] = src.numpy(); corr[:, 4:7] = tgt.numpy()
+    T0 = np.eye(4, dtype=np.float32); T0[:3, :3] = Rg.numpy(); T0[:3, 3] = tg.numpy() + 0.03
+    To, it_o, inl_o = oracle.post_refinement(T0, corr, 0.10, 20)
+    cd = torch.from_numpy(corr).to(DEV); off = torch.tensor([0, n], dtype=torch.int32, device=DEV); cnt = torch.tensor([n], dtype=torch.int32, device=DEV)
+    for mc in (n, 0):                       # cluster kernel / single-CTA kernel
+        T, it, inl = backend.post_refinement_batched(torch.from_numpy(T0)[None].to(DEV), cd, off, cnt, 0.10, 20, max_count=mc)
+        assert np.array_equal(T[0].cpu().numpy(), To) and int(it.item()) == it_o and int(inl.item()) == inl_o
+    # a mixed batch through the cluster kernel: a small pair next to the big one
+    corr2 = np.concatenate([corr[:900], corr]); off2 = torch.tensor([0, 900, 900 + n], dtype=torch.int32, device=DEV)
+    cnt2 = torch.tensor([900, n], dtype=torch.int32, device=DEV)
+    T2, _, _ = backend.post_refinement_batched(torch.from_numpy(np.stack([T0, T0])).to(DEV), torch.from_numpy(corr2).to(DEV), off2, cnt2, 0.10, 20, max_count=n)
+    Ts, _, _ = oracle.post_refinement(T0, corr[:900], 0.10, 20)
+    assert np.array_equal(T2[0].cpu().numpy(), Ts) and np.array_equal(T2[1].cpu().numpy(), To)
+
+
+def test_k1_algo_is_per_thread(backend):
+    """bfr_config_set is thread-local: a second host thread toggling the algorithm does not disturb this one, and both threads can launch"""
+    import threading
+    g = torch.Generator().manual_seed(2)
+    src = torch.nn.functional.normalize(torch.randn(800, 32, generator=g), dim=-1).to(DEV)
+    tgt = torch.nn.functional.normalize(torch.randn(900, 32, generator=g), dim=-1).to(DEV)
+    ref = backend.mutual_matching_device(src, tgt)["nn_s"].clone()
+    seen, errs = {}, []
+
+    def worker():
+        try:
+            seen["default"] = backend.get_k1_algo()
+            backend.set_k1_algo(backend.K1_FP32)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                for _ in range(20):
+                    r = backend.mutual_matching_device(src, tgt)
+                st.synchronize()
+            seen["same"] = bool(torch.equal(r["nn_s"], ref)); seen["algo"] = backend.get_k1_algo()
+        except Exception as e:              # noqa: BLE001
+            errs.append(e)
+
+    th = threading.Thread(target=worker); th.start()
+    for _ in range(20):
+        r = backend.mutual_matching_device(src, tgt)
+        assert backend.get_k1_algo() == backend.K1_TENSOR_FILTER
+    th.join()
+    torch.cuda.synchronize()
+    assert not errs and seen == {"default": 1, "same": True, "algo": 0} and torch.equal(r["nn_s"], ref)
 
 
 def test_register_pipeline_matches_oracle_and_recovers_pose(oracle, backend, algo):

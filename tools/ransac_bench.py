@@ -8,7 +8,7 @@ if os.environ.get("BFR_SO"): _lib.SO_PATH = os.path.abspath(os.environ["BFR_SO"]
 from buffer_b200 import backend as B, synthetic as S
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 1623
 splits = [int(x) for x in sys.argv[2:]] or [1, 2, 3, 4]
-c = S.CONFIGS[2]; N = c["gen"]["num_kpts"]; dev = "cuda:0"
+c = S.CONFIGS[int(os.environ.get("BFR_CFG", "2"))]; N = c["gen"]["num_kpts"]; dev = "cuda:0"
 parts = [S.make_pairs(min(128, P - p0), first_pair=p0, device=dev, **c["gen"]) for p0 in range(0, P, 128)]
 cat = lambda f: torch.cat([getattr(b, f) for b in parts], 0)
 src_des, tgt_des = cat("src_des").reshape(P * N, 32), cat("tgt_des").reshape(P * N, 32)
@@ -27,3 +27,9 @@ for s in splits:
     same = True if ref is None else bool(torch.equal(T, ref))
     if ref is None: ref = T.clone()
     print("splits %d: %.3f ms (min of 3 warm runs), identical to splits[0]: %s" % (s, min(ms[1:]), same))
+    L = _lib.lib()
+    if hasattr(L, "bfr_dbg_ransac_counters"):       # -DRS_TIMING variant: cycles summed over CTAs (thread 0's clock), 4 launches
+        import ctypes, numpy as np
+        o = np.zeros(8, dtype=np.uint64); L.bfr_dbg_ransac_counters(ctypes.c_void_p(o.ctypes.data))
+        tot, sc, fit, n, nsc = [float(x) for x in o[:5]]
+        print("  per CTA: total %.0f cycles = stage1 %.0f + fit %.0f + score %.0f; scored hypotheses/CTA %.1f" % (tot / n, (tot - fit) / n, (fit - sc) / n, sc / n, nsc / n))

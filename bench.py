@@ -6,8 +6,10 @@
 One "step" = one pass of the hot path (mutual-NN matching -> Philox RANSAC with 3-point Kabsch and inlier scoring ->
 weighted-Kabsch post-refinement) over one batch of synthetic fragment pairs.  Default workload = BASELINE.json
 configs[1]: 1,623 pairs x 5,000 keypoints x 32-d descriptors, 50,000 hypotheses per pair, 70 % outliers.
-N > 1 (torchrun): pairs are independent, every rank processes its own 1,623 pairs, no data-path collective (weak
-scaling); time = max over ranks.  Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md §bench).
+N > 1 (torchrun): STRONG scaling - the fixed workload is sharded by pair over the ranks, one all_gather of the poses inside the
+timed region; time = max over ranks (the weak-scaling number is reported beside it as `weak_scaling`).  Every run also registers
+BASELINE config 5's single 100k x 100k pair cooperatively on all ranks (`split_pair`: row-split matching + NCCL MAX all-reduce).
+Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md §bench).
 """
 import argparse
 import ctypes
@@ -44,6 +46,7 @@ def parse():
     ap.add_argument("--e2e-chunk", type=int, default=64, help="pairs per host->device chunk of the e2e leg (two chunks in flight on two streams)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-split-pair", action="store_true", help="skip the config-5 huge-pair leg (one 100k x 100k pair registered cooperatively by all ranks)")
     return ap.parse_args()
 
 
@@ -156,20 +159,106 @@ def run_reference(args, rank, world):
     ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, c, P),
+            "config": config_dict(args, c, P, 1),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": "%d pairs of the workload per step (same generator, seeds 0..), whole back end" % sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def config_dict(args, c, P):
-    return {"workload": "BASELINE.json configs[%d]: %d pairs/GPU x %d keypoints x 32-d, %d RANSAC hypotheses/pair, outlier ratio %s"
+def config_dict(args, c, P, world=1):
+    return {"workload": "BASELINE.json configs[%d]: %d pairs x %d keypoints x 32-d, %d RANSAC hypotheses/pair, outlier ratio %s"
                         % (args.config - 1, P, c["gen"]["num_kpts"], c["hypotheses"], c["gen"].get("outlier_ratio")),
-            "pairs_per_gpu": P, "keypoints": c["gen"]["num_kpts"], "desc_dim": 32, "hypotheses": c["hypotheses"],
-            "dist_th": c["dist_th"], "similar_th": c["similar_th"], "refine_iters": 20,
-            "cache": "inputs (%.2f GB/GPU) exceed the 126 MB L2; every step re-reads them from HBM" % (P * c["gen"]["num_kpts"] * 2 * (32 + 3) * 4 / 1e9),
-            "parallelism": "pairs sharded by rank, no collective in the data path"}
+            "pairs_total": P, "pairs_per_gpu": (P + world - 1) // world, "keypoints": c["gen"]["num_kpts"], "desc_dim": 32, "hypotheses": c["hypotheses"],
+            "dist_th": c["dist_th"], "similar_th": c["similar_th"], "refine_iters": 20, "confidence": 1.0,
+            "cache": "inputs (%.2f GB in total) exceed the 126 MB L2; every step re-reads them from HBM" % (P * c["gen"]["num_kpts"] * 2 * (32 + 3) * 4 / 1e9),
+            "parallelism": "the FIXED workload is sharded by pair over the ranks (contiguous blocks); no collective in the data path, one all_gather of "
+                           "18 floats per pair (poses + counts) inside the timed region" if world > 1 else "single GPU"}
+
+
+def gen_range(c, start, end, device, chunk=128):
+    """pairs [start, end) of the workload, generated in the workload's global 128-pair chunks so that a pair's data does not depend on
+    how the workload is sharded -> PairBatch on `device`"""
+    parts = []
+    for k in range(start // chunk, (end + chunk - 1) // chunk):
+        p0 = k * chunk
+        b = S.make_pairs(chunk, first_pair=p0, device=device, **c["gen"])
+        lo, hi = max(start, p0) - p0, min(end, p0 + chunk) - p0
+        parts.append([getattr(b, f)[lo:hi] for f in ("src_des", "tgt_des", "src_xyz", "tgt_xyz", "T_gt", "perm", "inlier")])
+        del b
+    return S.PairBatch(*[torch.cat([p[i] for p in parts], 0).contiguous() for i in range(7)])
+
+
+def timed(fn, steps, barrier, dev, world, dist):
+    """K calls of fn bracketed by barrier + synchronize, device-timed, max over ranks -> ms per step"""
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        out = fn()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() / steps, out
+
+
+def split_pair_leg(args, dev, rank, world, dist, barrier, n_kpts=100000):
+    """BASELINE config 5's single huge pair (100k x 100k keypoints, 50k hypotheses) registered cooperatively by all ranks: K1 row-split +
+    NCCL MAX all-reduce of the packed bests, RANSAC split by hypothesis + 8-byte MAX all-reduce (buffer_b200.dist.HugePairSplit)"""
+    from buffer_b200 import backend as B, dist as D
+    c5 = S.CONFIGS[5]
+    g = dict(c5["gen"], num_kpts=n_kpts)
+    b = S.make_pairs(1, first_pair=10 ** 6, device=dev, **g)          # same seed on every rank: the pair is replicated
+    hp = D.HugePairSplit(b.src_des[0], b.src_xyz[0], b.tgt_des[0], b.tgt_xyz[0])
+    kw = dict(hypotheses=c5["hypotheses"], dist_th=c5["dist_th"], similar_th=c5["similar_th"], refine_thr=c5["refine_thr"], seed=0, pair_id=10 ** 6)
+    for _ in range(3):
+        hp.run(**kw)
+    ms, (T, cnt, inl, bh) = timed(lambda: hp.run(**kw), max(args.steps, 5), barrier, dev, world, dist)
+    out = {"keypoints": n_kpts, "hypotheses": c5["hypotheses"], "ms": ms, "mutual_matches": int(cnt.item()), "ransac_inliers": int(inl.item())}
+    rec, rte, rre = S.registration_recall(T.cpu(), b.T_gt.cpu())
+    out["recall"] = rec; out["rte_m"] = float(rte.max())
+    if world > 1:
+        ev = {k: torch.cuda.Event(enable_timing=True) for k in ("k1_ar0", "k1_ar1", "rs_ar0", "rs_ar1")}
+        barrier()
+        hp.run(events=ev, **kw)
+        barrier()
+        ar = torch.tensor([ev["k1_ar0"].elapsed_time(ev["k1_ar1"]), ev["rs_ar0"].elapsed_time(ev["rs_ar1"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+        out["allreduce_packed_bests_ms"] = ar[0].item(); out["allreduce_packed_bests_bytes"] = int(hp.k1.packed.numel() * 8)
+        out["allreduce_ransac_best_ms"] = ar[1].item(); out["allreduce_share"] = (ar[0].item() + ar[1].item()) / ms
+        # the same pair on ONE GPU (this rank alone, no collective): must give the same bits
+        solo = D.HugePairSplit(b.src_des[0], b.src_xyz[0], b.tgt_des[0], b.tgt_xyz[0])
+        solo.world, solo.rank = 1, 0
+        T1, cnt1, inl1, bh1 = solo.run(**kw)
+        same = torch.tensor([int(torch.equal(T, T1) and torch.equal(cnt, cnt1) and torch.equal(inl, inl1) and torch.equal(bh, bh1))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        out["bit_equal_to_one_gpu"] = bool(same.item())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(3):
+            solo.run(**kw)
+        e1.record(); torch.cuda.synchronize()
+        out["ms_one_gpu_same_run"] = e0.elapsed_time(e1) / 3
+        out["design"] = ("K1 row blocks split over ranks, %d-byte MAX all-reduce of the packed bests (NCCL over NVLink), select replicated; RANSAC hypotheses split, "
+                         "8-byte MAX all-reduce, winner regenerated locally; refinement replicated" % out["allreduce_packed_bests_bytes"])
+    return out
+
+
+def torch_baseline(c, batch, threads, timed_hypotheses=2000):
+    """BASELINE config 1: the reference's CPU torch path (oracle/torch_ref.py) on the first pair of the workload, host cores"""
+    from oracle import oracle as O, torch_ref as TR
+    h = [getattr(batch, f)[0].cpu() for f in ("src_des", "tgt_des", "src_xyz", "tgt_xyz")]
+    samples_fn = lambda K, n: np.stack([O.sample3(0, 0, i, K) for i in range(n)]).astype(np.int64)
+    r = TR.time_pair(h[0], h[1], h[2], h[3], samples_fn, c["hypotheses"], timed_hypotheses, c["dist_th"], c["similar_th"], c["refine_thr"], threads)
+    T = r.pop("T")
+    ok, rte, rre = S.registration_recall(torch.from_numpy(T)[None], batch.T_gt[:1].cpu())
+    r.update({"value": 1.0 / r["total_s"], "unit": UNIT, "cores": threads, "torch_threads": torch.get_num_threads(), "kind": "reference torch path, restated (oracle/torch_ref.py)",
+              "sample": "pair 0 of the workload: torch.cdist + min matching (best of 3), Open3D-semantics Python loop on torch.svd Kabsch for the first %d of %d hypotheses "
+                        "(time scaled linearly to %d; Open3D's own C++ loop is a third-party wheel that is absent), post_refinement with diag_embed" % (timed_hypotheses, c["hypotheses"], c["hypotheses"]),
+              "recall_on_sample": ok})
+    return r
 
 
 def main():
@@ -184,17 +273,20 @@ def main():
         bind_to_gpu_cpus(local)              # pinned host buffers of the e2e leg are then first-touched on the GPU's own NUMA node
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    from buffer_b200 import _lib, backend as B
+    from buffer_b200 import _lib, backend as B, dist as D
     L = _lib.lib()
     B.set_k1_algo(args.k1_algo)
 
-    c, P = workload(args.config, args.pairs)
+    c, P_total = workload(args.config, args.pairs)
     N = c["gen"]["num_kpts"]
     kw = dict(hypotheses=c["hypotheses"], dist_th=c["dist_th"], similar_th=c["similar_th"], refine_thr=c["refine_thr"], refine_iters=20, seed=0)
-    batch = gen_pairs(c, P, rank * P, dev)                       # resident in HBM before the timed region
+    p_lo, p_hi = D.shard_range(P_total, rank, world)              # STRONG scaling: the fixed workload is sharded by pair
+    P = p_hi - p_lo
+    batch = gen_range(c, p_lo, p_hi, dev)                         # resident in HBM before the timed region
     src_des = batch.src_des.reshape(P * N, 32); tgt_des = batch.tgt_des.reshape(P * N, 32)
     src_xyz = batch.src_xyz.reshape(P * N, 3); tgt_xyz = batch.tgt_xyz.reshape(P * N, 3)
     off = (torch.arange(P + 1, dtype=torch.int32) * N).to(dev)
@@ -207,7 +299,10 @@ def main():
         torch.cuda.synchronize()
 
     def step():
-        return B.register_batched(src_des, src_xyz, off, tgt_des, tgt_xyz, off, N, N, pair_id_base=rank * P, **kw)
+        T, nm, ni = B.register_batched(src_des, src_xyz, off, tgt_des, tgt_xyz, off, N, N, pair_id_base=p_lo, **kw)
+        if world > 1:
+            return D.gather_pair_results(T, nm, ni, P_total) + (T,)     # every rank ends up with all poses
+        return T, nm, ni, T
 
     peak_tf = fp32_peak_tflops(dev)
     for _ in range(max(args.warmup, 3)):
@@ -234,9 +329,28 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = t.item() / args.steps
-    value = world * P / (ms_step * 1e-3)
-    T, nm, ni = out
-    recall, rte, rre = S.registration_recall(T.cpu(), batch.T_gt.cpu())
+    value = P_total / (ms_step * 1e-3)
+    T_all, nm, ni, T = out
+    ok_local, rte, rre = S.registration_recall(T.cpu(), batch.T_gt.cpu())
+    q = torch.tensor([ok_local * P, float(P)], dtype=torch.float64, device=dev)
+    qmax = torch.tensor([float(rte.max()) if P else 0.0, float(rre.max()) if P else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(q); dist.all_reduce(qmax, op=dist.ReduceOp.MAX)
+    recall = (q[0] / q[1]).item()
+
+    # ---- weak-scaling leg (N > 1 only; the headline above is STRONG scaling): every rank runs the full workload of its own pairs ----
+    weak = None
+    if world > 1:
+        wb = gen_range(c, rank * P_total, (rank + 1) * P_total, dev)
+        wargs = (wb.src_des.reshape(-1, 32), wb.src_xyz.reshape(-1, 3), (torch.arange(P_total + 1, dtype=torch.int32) * N).to(dev),
+                 wb.tgt_des.reshape(-1, 32), wb.tgt_xyz.reshape(-1, 3))
+        wstep = lambda: B.register_batched(wargs[0], wargs[1], wargs[2], wargs[3], wargs[4], wargs[2], N, N, pair_id_base=rank * P_total, **kw)
+        for _ in range(2):
+            wstep()
+        wms, _ = timed(wstep, args.steps, barrier, dev, world, dist)
+        weak = {"value": world * P_total / (wms * 1e-3), "unit": UNIT, "ms_per_step": wms, "pairs_per_gpu": P_total,
+                "note": "every rank processes its own %d pairs, no collective" % P_total}
+        del wb, wargs
 
     # ---- extra leg (outside the timed region): the all-FP32 mutual-NN kernel on the same data, for the FP32 roofline --------
     fp32_ms = None
@@ -278,11 +392,23 @@ def main():
             nvalid.zero_()
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ea.record()
-            B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], seed=0, pair_id_base=rank * P, valid_count=nvalid)
+            B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], seed=0, pair_id_base=p_lo, valid_count=nvalid)
             eb.record(); eb.synchronize()
             ransac_ms.append(ea.elapsed_time(eb))
         ransac_ms = min(ransac_ms)
         hv_total = float(nvalid.sum().item()); c_mean = float(rm["n_mutual"].float().mean().item())
+        # Open3D's confidence early exit (the reference's 3DMatch setting, ThreeDMatch/config.py:65): same call with confidence = 0.999
+        conf_ms = []
+        for i in range(3):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            bp_c = B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], seed=0, pair_id_base=p_lo, confidence=0.999)
+            eb.record(); eb.synchronize()
+            conf_ms.append(ea.elapsed_time(eb))
+        Tc_, inl_c, _ = B.ransac_finalize_batched(rm["corr"], off, rm["n_mutual"], bp_c, c["dist_th"], c["similar_th"], seed=0, pair_id_base=p_lo)
+        conf_recall, _, _ = S.registration_recall(Tc_.cpu(), batch.T_gt.cpu())
+        conf = {"confidence": 0.999, "ms_per_launch": min(conf_ms), "speedup_vs_all_hypotheses": ransac_ms / min(conf_ms), "recall_before_refinement": conf_recall,
+                "inliers_mean": float(inl_c.float().mean())}
         del rm
 
     # ---- e2e: host (pinned) buffers -> poses on the host, copies inside the timed region ---------------------------
@@ -292,8 +418,8 @@ def main():
         pin = lambda x: x.contiguous().pin_memory()
         h = [pin(hb.src_des), pin(hb.src_xyz), pin(hb.tgt_des), pin(hb.tgt_xyz)]
         Th = torch.empty(P, 4, 4).pin_memory(); nmh = torch.empty(P, dtype=torch.int32).pin_memory(); nih = torch.empty(P, dtype=torch.int32).pin_memory()
-        chunk = min(P, args.e2e_chunk)
-        reg = B.HostRegistrar(chunk, N, N, dev, ransac_splits=None, **kw)
+        chunk = max(1, min(P, args.e2e_chunk))
+        reg = B.HostRegistrar(chunk, N, N, dev, ransac_splits=None, pair_id_base=p_lo, **kw)
         for _ in range(2):
             reg.run(*h, Th, nmh, nih)
         barrier()
@@ -306,23 +432,36 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         same = bool(torch.equal(Th, T.cpu()))
-        # context for the e2e number: the bare host->device copy of one step's inputs (pinned, one stream), outside the timed region
+        # the platform ceiling: the bare host->device copy of one step's inputs, ALL ranks copying at the same time (pinned, one stream each)
         dbuf = [torch.empty_like(x, device=dev) for x in h]
-        ca, cb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         h2d_ms = []
         for _ in range(3):
+            ca, cb_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
             ca.record()
             for d_, x in zip(dbuf, h):
                 d_.copy_(x, non_blocking=True)
             cb_.record(); cb_.synchronize()
-            h2d_ms.append(ca.elapsed_time(cb_))
+            tcp = torch.tensor([ca.elapsed_time(cb_)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tcp, op=dist.ReduceOp.MAX)
+            h2d_ms.append(tcp.item())
         del dbuf
         h2d_ms = min(h2d_ms)
-        e2e = {"value": world * P * args.steps / tt.item(), "unit": UNIT, "ms_per_step": tt.item() / args.steps * 1e3,
-               "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gbs": sum(x.numel() * 4 for x in h) / (h2d_ms * 1e-3) * 1e-9,
-               "h2d_bytes_per_step": int(sum(x.numel() * 4 for x in h)), "d2h_bytes_per_step": int(Th.numel() * 4 + nmh.numel() * 4 + nih.numel() * 4),
-               "api": "buffer_b200.backend.HostRegistrar.run -> bfr_register_uniform_host (pinned host buffers, %d-pair chunks on 2 streams)" % chunk,
+        step_ms = tt.item() / args.steps * 1e3
+        bytes_in = int(sum(x.numel() * 4 for x in h)); bytes_out = int(Th.numel() * 4 + nmh.numel() * 4 + nih.numel() * 4)
+        tot = torch.tensor([float(bytes_in), float(bytes_out)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tot)
+        e2e = {"value": P_total * args.steps / tt.item(), "unit": UNIT, "ms_per_step": step_ms,
+               "h2d_concurrent_copy_floor_ms": h2d_ms, "h2d_concurrent_copy_gbs_per_gpu": bytes_in / (h2d_ms * 1e-3) * 1e-9,
+               "frac_of_concurrent_copy_floor": h2d_ms / step_ms,
+               "h2d_bytes_per_step": int(tot[0].item()), "d2h_bytes_per_step": int(tot[1].item()),
+               "api": "buffer_b200.backend.HostRegistrar.run -> ONE bfr_register_uniform_host_chunked call per rank and step (pinned host buffers, %d-pair chunks on 2 streams); "
+                      "each rank's poses land in its own host buffer" % chunk,
                "poses_equal_device_path": same, "launches_per_step": 8 * ((P + chunk - 1) // chunk)}
+
+    split_pair = None if args.no_split_pair else split_pair_leg(args, dev, rank, world, dist, barrier)
 
     if rank == 0:
         flops_k1 = 2.0 * N * N * 32 * P
@@ -331,7 +470,10 @@ def main():
         tpath = os.path.join(ROOT, "profiles", "k1_tc_traffic.json" if args.k1_algo == 1 else "k1_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+                tj = json.load(open(tpath))
+                traffic = tj.get("dram_bytes_per_launch")
+                if traffic is not None and tj.get("pairs"):
+                    traffic = traffic * P / tj["pairs"]       # static: taken from the committed ncu capture, scaled to this launch's pairs
             except Exception:
                 traffic = None
         mp = _measured_peaks()
@@ -348,6 +490,7 @@ def main():
             mma_floor_ms = tiles / 148.0 * 345.0 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)
             roof = {"kernel": "k1_tc_kernel (one launch, both directions: tcgen05 f16 filter, 128x256 accumulator tiles in TMEM + exact FP32 re-check)", "bound": "tensor",
                     "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": traffic,
+                    "traffic_source": "static: dram__bytes_read+write of the committed ncu --set full capture (profiles/k1_tc_traffic.json), scaled by pairs; not measured in this run",
                     "k1_ms_per_launch": k1_ms, "k1_share_of_step": k1_ms / ms_step, "algorithmic_flops_per_launch": flops_k1,
                     "executed_tensor_flops_per_launch": 2 * flops_k1,
                     "peak_source": "dense 16-bit tensor peak = measured cuBLAS bf16 burst in MEASURED_PEAKS.json (f16 and bf16 MMAs run at the same rate) (%s)" % ("measured" if mp.get("bf16_tflops") else "fallback 1.59 PF"),
@@ -360,22 +503,27 @@ def main():
         else:
             roof = dict(fp32_roof, traffic=traffic, k1_ms_per_launch=k1_ms, k1_share_of_step=k1_ms / ms_step, algorithmic_flops_per_launch=flops_k1)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args, c, P), "clocks": clocks, "gpu_launches": 7 * args.steps,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, c, P_total, world), "clocks": clocks, "gpu_launches": 8 * args.steps,
                 "roofline": roof, "roofline_fp32_path": fp32_roof,
                 "roofline_ransac": {"kernel": "ransac_kernel (Philox + Kabsch + checkers + inlier scoring)", "bound": "fp32", "ms_per_launch": ransac_ms,
                                     "valid_hypotheses_per_pair": hv_total / P, "hypotheses_per_pair": c["hypotheses"], "correspondences_per_pair": c_mean,
                                     "algorithmic_flops_per_launch": 28.0 * hv_total * c_mean, "achieved": 28.0 * hv_total * c_mean / (ransac_ms * 1e-3) * 1e-12,
                                     "peak": peak_tf, "unit": "TFLOP/s", "frac": 28.0 * hv_total * c_mean / (ransac_ms * 1e-3) * 1e-12 / peak_tf,
                                     "hypotheses_per_s": P * c["hypotheses"] / (ransac_ms * 1e-3),
-                                    "streaming_model_gbs": 24.0 * c_mean * hv_total / 256.0 / (ransac_ms * 1e-3) * 1e-9,
-                                    "streaming_model_note": "bytes = 24*C*H_valid/T_h with T_h = 256 hypotheses per CTA pass; the correspondences stream from L2/shared memory, "
-                                                            "not HBM (compulsory HBM traffic is 32*C bytes per pair), so the kernel is FP32-issue-bound, not HBM-bound"},
-                "quality": {"registration_recall": recall, "rte_max_m": float(rte.max()), "rre_max_deg": float(rre.max()),
+                                    "streaming_model_gbs": 24.0 * c_mean * hv_total / 512.0 / (ransac_ms * 1e-3) * 1e-9,
+                                    "streaming_model_note": "bytes = 24*C*H_valid/T_h with T_h = 512 hypotheses per CTA pass; a pair's correspondences are loaded ONCE into shared memory "
+                                                            "(compulsory HBM traffic is 32*C bytes per pair), so the kernel is FP32-issue-bound, not HBM-bound",
+                                    "open3d_confidence_exit": conf},
+                "quality": {"registration_recall": recall, "rte_max_m": qmax[0].item(), "rre_max_deg": qmax[1].item(),
                             "mutual_matches_mean": float(nm.float().mean()), "ransac_inliers_mean": float(ni.float().mean())}}
+        if weak is not None:
+            line["weak_scaling"] = weak
         if e2e is not None:
             line["e2e"] = e2e
-        if not args.no_cpu:
+        if split_pair is not None:
+            line["split_pair"] = split_pair
+        if not args.no_cpu and world == 1:
             threads = os.cpu_count() or 1
             sample = min(P, args.cpu_sample_pairs or max(threads * 16, 64))
             hs = S.PairBatch(*[getattr(batch, f)[:sample].cpu() for f in ("src_des", "tgt_des", "src_xyz", "tgt_xyz", "T_gt", "perm", "inlier")])
@@ -384,6 +532,10 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt,
                                     "sample": "first %d pairs of the same workload, whole back end (oracle/bfr_oracle.c, OpenMP over pairs)" % sample,
                                     "poses_bit_identical_to_gpu": same}
+            try:
+                line["cpu_baseline_torch"] = torch_baseline(c, batch, threads)
+            except Exception as exc:             # noqa: BLE001 - a baseline leg must not take the bench line down
+                line["cpu_baseline_torch"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

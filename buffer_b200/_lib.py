@@ -36,6 +36,7 @@ SIGNATURES = {
     "bfr_register_batched": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _u64, _u32, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_register_host_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "bfr_register_uniform_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u64, _u32, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "bfr_register_uniform_host_chunked": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _u64, _u32, _f, _f, _f, _f, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp, _i]),
     "bfr_get_matching_indices_workspace_bytes": (_sz, [_i]),
     "bfr_get_matching_indices": (_i, [_vp, _i, _vp, _i, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_svd3_batched": (_i, [_vp, _i, _vp, _vp, _vp, _vp]),

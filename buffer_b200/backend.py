@@ -555,12 +555,13 @@ def register_uniform(src_des, src_xyz, tgt_des, tgt_xyz, **kw):
 
 class HostRegistrar:
     """End-to-end path for inputs that live in (pinned) HOST memory: chunks of pairs are copied host->device, processed
-    and their poses copied back on two alternating CUDA streams, so copies overlap compute (bfr_register_uniform_host).
-    This is the call bench.py times for the `e2e` number."""
+    and their poses copied back on two alternating CUDA streams, so copies overlap compute.  The chunk loop runs inside the library
+    (ONE bfr_register_uniform_host_chunked call per batch).  This is the call bench.py times for the `e2e` number."""
 
     def __init__(self, chunk_pairs, M, N, device, hypotheses=50000, dist_th=0.10, similar_th=0.8, refine_thr=0.10, refine_iters=20,
-                 seed=0, ransac_splits=None, n_streams=2, confidence=1.0):
+                 seed=0, ransac_splits=None, n_streams=2, confidence=1.0, pair_id_base=0):
         self.chunk, self.M, self.N, self.dev = chunk_pairs, M, N, torch.device(device)
+        self.pair_id_base = pair_id_base
         self.kw = dict(hypotheses=hypotheses, dist_th=dist_th, similar_th=similar_th, refine_thr=refine_thr, refine_iters=refine_iters, seed=seed,
                        confidence=confidence)
         self.splits = ransac_splits if ransac_splits is not None else _default_splits(chunk_pairs)
@@ -576,23 +577,22 @@ class HostRegistrar:
             return self._run(src_des, src_xyz, tgt_des, tgt_xyz, T_out, n_mutual_out, n_inliers_out)
 
     def _run(self, src_des, src_xyz, tgt_des, tgt_xyz, T_out, n_mutual_out, n_inliers_out):
+        import ctypes as C
         L = _lib.lib()
         P = src_des.shape[0]
         k = self.kw
         cur = torch.cuda.current_stream(self.dev)
         for s in self.streams:
             s.wait_stream(cur)
-        for ci, p0 in enumerate(range(0, P, self.chunk)):
-            n = min(self.chunk, P - p0)
-            s = self.streams[ci % len(self.streams)]
-            ws = self.ws[ci % len(self.streams)]
-            _lib.check(L.bfr_register_uniform_host(src_des[p0].data_ptr(), src_xyz[p0].data_ptr(), tgt_des[p0].data_ptr(), tgt_xyz[p0].data_ptr(),
-                                                   n, self.M, self.N, DESC_DIM, int(k["hypotheses"]), int(k["seed"]), int(p0),
-                                                   float(k["dist_th"]), float(k["similar_th"]), float(k["confidence"]), float(k["refine_thr"]), int(k["refine_iters"]),
-                                                   int(self.splits), T_out[p0].data_ptr(),
-                                                   0 if n_mutual_out is None else n_mutual_out[p0:].data_ptr(),
-                                                   0 if n_inliers_out is None else n_inliers_out[p0:].data_ptr(),
-                                                   ws.data_ptr(), ws.numel(), s.cuda_stream), "bfr_register_uniform_host")
+        ns = len(self.streams)
+        ws = (C.c_void_p * ns)(*[w.data_ptr() for w in self.ws])
+        st = (C.c_void_p * ns)(*[s.cuda_stream for s in self.streams])
+        _lib.check(L.bfr_register_uniform_host_chunked(src_des.data_ptr(), src_xyz.data_ptr(), tgt_des.data_ptr(), tgt_xyz.data_ptr(), P, self.M, self.N, DESC_DIM,
+                                                       int(self.chunk), int(k["hypotheses"]), int(k["seed"]), int(self.pair_id_base), float(k["dist_th"]),
+                                                       float(k["similar_th"]), float(k["confidence"]), float(k["refine_thr"]), int(k["refine_iters"]), int(self.splits),
+                                                       T_out.data_ptr(), 0 if n_mutual_out is None else n_mutual_out.data_ptr(),
+                                                       0 if n_inliers_out is None else n_inliers_out.data_ptr(), ws, min(w.numel() for w in self.ws), st, ns),
+                   "bfr_register_uniform_host_chunked")
         for s in self.streams:
             s.synchronize()
         return T_out

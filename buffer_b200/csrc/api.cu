@@ -335,6 +335,31 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
     return BFR_OK;
 }
 
+int bfr_register_uniform_host_chunked(const float* src_des_host, const float* src_xyz_host, const float* tgt_des_host, const float* tgt_xyz_host,
+                                      int P, int M, int N, int D, int chunk_pairs, int hypotheses, uint64_t seed, uint32_t pair_id_base,
+                                      float dist_th, float similar_th, float confidence, float refine_thr, int refine_iters, int ransac_splits,
+                                      float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host,
+                                      void* const* ws, size_t ws_bytes_each, void* const* streams, int n_streams)
+{
+    if (P == 0) return BFR_OK;
+    if (!ws || !streams) return BFR_E_NULL;
+    if (P < 0 || chunk_pairs < 1 || n_streams < 1 || M < 0 || N < 0) return BFR_E_SIZE;
+    // chunk c goes to stream c % n_streams with that stream's workspace: the copies of one chunk overlap the kernels of the other streams'
+    // chunks, and the reuse of a workspace is ordered by its stream
+    int c = 0;
+    for (int p0 = 0; p0 < P; p0 += chunk_pairs, ++c) {
+        const int n = P - p0 < chunk_pairs ? P - p0 : chunk_pairs;
+        const int k = c % n_streams;
+        const int rc = bfr_register_uniform_host(src_des_host + (size_t)p0 * M * D, src_xyz_host + (size_t)p0 * M * 3, tgt_des_host + (size_t)p0 * N * D,
+                                                 tgt_xyz_host + (size_t)p0 * N * 3, n, M, N, D, hypotheses, seed, pair_id_base + (uint32_t)p0, dist_th, similar_th,
+                                                 confidence, refine_thr, refine_iters, ransac_splits, T_out_host ? T_out_host + (size_t)p0 * 16 : nullptr,
+                                                 n_mutual_host ? n_mutual_host + p0 : nullptr, n_inliers_host ? n_inliers_host + p0 : nullptr,
+                                                 ws[k], ws_bytes_each, streams[k]);
+        if (rc != BFR_OK) return rc;
+    }
+    return BFR_OK;
+}
+
 size_t bfr_get_matching_indices_workspace_bytes(int N) { return knn3_workspace_bytes(N); }
 
 int bfr_get_matching_indices(const float* source, int N, const float* target, int M, const float* relt_pose, float search_voxel_size,

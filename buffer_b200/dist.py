@@ -4,11 +4,15 @@ The path shards by fragment pair (the reference processes one pair per forward, 
 ThreeDMatch/config.py:21, dataloader.py:119), so the data path has NO collective: rank r owns a contiguous block of
 pairs and results are collected with one all_gather of 18 numbers per pair (NCCL over NVLink; latency-bound).
 
-One huge pair (BASELINE config 5, 100k x 100k keypoints) is split by HYPOTHESIS instead: every rank evaluates
-h in [r*H/W, (r+1)*H/W) of the same Philox stream and the 8-byte packed best (count << 32 | ~h) is max-all-reduced;
-because the RNG is counter-based, every rank then regenerates the winning fit locally — no broadcast of R, t.
+One huge pair (BASELINE config 5, 100k x 100k keypoints) replicated on every rank is split twice (HugePairSplit):
+  * matching by ROW BLOCKS - 95 % of its work: rank r runs the fused distance + arg-max kernel on its 1/W share of the source row
+    blocks (src->tgt direction) and of the target row blocks (tgt->src direction); the packed bests (key << 32 | ~index, 8 bytes per
+    row of either side: 1.6 MB at 100k x 100k) are max-all-reduced over NVLink (NCCL), then every rank decodes / compacts them;
+  * RANSAC by HYPOTHESIS: every rank evaluates h in [r*H/W, (r+1)*H/W) of the same Philox stream and the 8-byte packed best
+    (count << 32 | ~h) is max-all-reduced; because the RNG is counter-based, every rank then regenerates the winning fit locally -
+    no broadcast of R, t.  The refinement (<2 % of the work) is replicated.
 
-The compute callables are injectable so the host logic is testable on CPU with the gloo backend (tests/test_dist_cpu.py).
+The compute callables are injectable so the host logic is testable on CPU with the gloo backend (tests/test_host_cpu.py).
 """
 import torch
 import torch.distributed as dist
@@ -76,3 +80,54 @@ def ransac_split_hypotheses(corr, corr_off, corr_cnt, hypotheses, dist_th, simil
     if world > 1:
         dist.all_reduce(best, op=dist.ReduceOp.MAX, group=group)     # packed value < 2^63: signed max == unsigned max
     return finalize_fn(corr, corr_off, corr_cnt, best, dist_th, similar_th, seed=seed, pair_id_base=pair_id_base)
+
+
+def all_reduce_max_u64(packed_i64, group=None):
+    """unsigned 64-bit MAX of an int64-typed view: flipping bit 63 maps the unsigned order onto the signed one NCCL / gloo reduce"""
+    packed_i64 ^= -0x8000000000000000
+    dist.all_reduce(packed_i64, op=dist.ReduceOp.MAX, group=group)
+    packed_i64 ^= -0x8000000000000000
+    return packed_i64
+
+
+class HugePairSplit:
+    """One pair, replicated on every rank, registered cooperatively (see module docstring).  All device work is enqueued on the current
+    stream; there is no host sync.  `timers` (optional dict) receives CUDA events around the two collectives."""
+
+    def __init__(self, src_des, src_xyz, tgt_des, tgt_xyz, group=None):
+        from . import backend
+        self.B = backend
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        M, N = src_des.shape[0], tgt_des.shape[0]
+        dev = src_des.device
+        self.M, self.N = M, N
+        self.src_xyz, self.tgt_xyz = src_xyz, tgt_xyz
+        self.src_off = torch.tensor([0, M], dtype=torch.int32).to(dev)
+        self.tgt_off = torch.tensor([0, N], dtype=torch.int32).to(dev)
+        self.k1 = backend.MutualNNSplit(src_des, tgt_des, self.src_off, self.tgt_off, M, N)
+
+    def run(self, hypotheses=50000, dist_th=0.10, similar_th=0.8, refine_thr=0.10, refine_iters=20, seed=0, pair_id=0, events=None):
+        B, world, rank = self.B, self.world, self.rank
+        packed = self.k1.partial(rank, world)
+        if world > 1:
+            if events is not None:
+                events["k1_ar0"].record()
+            all_reduce_max_u64(packed, self.group)
+            if events is not None:
+                events["k1_ar1"].record()
+        m = self.k1.select(self.src_xyz, self.tgt_xyz, want_nn=False, want_mids=False)
+        corr, cnt = m["corr"], m["n_mutual"]
+        h0, h1 = hypothesis_range(hypotheses, rank, world)
+        best = B.ransac_batched(corr, self.src_off, cnt, hypotheses, dist_th, similar_th, seed=seed, pair_id_base=pair_id, h_begin=h0, h_end=h1)
+        if world > 1:
+            if events is not None:
+                events["rs_ar0"].record()
+            dist.all_reduce(best, op=dist.ReduceOp.MAX, group=self.group)        # packed value < 2^63: signed max == unsigned max
+            if events is not None:
+                events["rs_ar1"].record()
+        T, inl, bh = B.ransac_finalize_batched(corr, self.src_off, cnt, best, dist_th, similar_th, seed=seed, pair_id_base=pair_id)
+        if refine_iters > 0:
+            T, _, _ = B.post_refinement_batched(T, corr, self.src_off, cnt, refine_thr, refine_iters, max_count=min(self.M, self.N))
+        return T, cnt, inl, bh

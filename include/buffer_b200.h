@@ -177,6 +177,16 @@ int bfr_register_uniform_host(const float* src_des_host, const float* src_xyz_ho
                               float dist_th, float similar_th, float confidence, float refine_thr, int refine_iters, int ransac_splits,
                               float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host, void* ws, size_t ws_bytes, void* stream);
 
+/* The whole job in ONE call: the P pairs are cut into chunks of chunk_pairs pairs, chunk c is enqueued (copies + kernels + copies back,
+ * exactly bfr_register_uniform_host with pair ids pair_id_base + first pair of the chunk) on streams[c % n_streams] with workspace
+ * ws[c % n_streams] (each of ws_bytes_each >= bfr_register_host_workspace_bytes(chunk_pairs, M, N, D)); with two or more streams the
+ * host<->device copies of one chunk overlap the kernels of another.  Asynchronous: synchronise every stream before reading the outputs. */
+int bfr_register_uniform_host_chunked(const float* src_des_host, const float* src_xyz_host, const float* tgt_des_host, const float* tgt_xyz_host,
+                                      int P, int M, int N, int D, int chunk_pairs, int hypotheses, uint64_t seed, uint32_t pair_id_base,
+                                      float dist_th, float similar_th, float confidence, float refine_thr, int refine_iters, int ransac_splits,
+                                      float* T_out_host, int32_t* n_mutual_host, int32_t* n_inliers_host,
+                                      void* const* ws, size_t ws_bytes_each, void* const* streams, int n_streams);
+
 /* ---- "next" rows ------------------------------------------------------------------------------------
  * bfr_get_matching_indices replaces buffer.get_matching_indices (models/BUFFER.py:361-380; twins ThreeDMatch/dataset.py:14-22,
  * ThreeDMatch/trainer.py:38-54): source [N][3] is transformed by relt_pose (DEVICE pointer to a row-major 4x4), every

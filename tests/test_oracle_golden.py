@@ -247,3 +247,23 @@ def test_config1_full_size_equals_reference(oracle):
     T2, nv, ni = oracle.pose_from_votes_batched(corr, off, cnt_, ind.numpy(), ss_R.numpy(), tt_R.numpy(), H, seed, pid, 0.1, 0.8, 1.0, 0.1, 20)
     assert nv[0] == len(g["vote_inlier_ind"]) and abs(int(ni[0]) - int(g["sub_best_count"])) <= 1
     assert rot_err(T2[0, :3, :3], g["sub_T_refined"][:3, :3]) < 1e-5 and np.abs(T2[0, :3, 3] - g["sub_T_refined"][:3, 3]).max() < 1e-5
+
+
+def test_torch_restatement_equals_reference():
+    """oracle/torch_ref.py (the reference's CPU torch path restated for timing in bench.py) against the reference's own outputs"""
+    from oracle import torch_ref as TR
+    g = load("mutual_matching")
+    s, t = TR.mutual_matching(torch.from_numpy(g["src_des"]), torch.from_numpy(g["tgt_des"]))
+    assert np.array_equal(s, g["s_mids"]) and np.array_equal(t, g["t_mids"])
+    g = load("rigid_transform_3d")
+    for case in ("n3", "n200_w", "n200_wthr", "mirror"):
+        w = torch.from_numpy(g[case + "_w"].copy()) if case + "_w" in g.files else None
+        T = TR.kabsch(torch.from_numpy(g[case + "_A"]), torch.from_numpy(g[case + "_B"]), w, float(g[case + "_thr"])).numpy()
+        assert np.abs(T - g[case + "_T"]).max() < 1e-5
+    g = load("post_refinement")
+    T = TR.post_refinement(torch.from_numpy(g["T0"]), torch.from_numpy(g["src"]), torch.from_numpy(g["tgt"]), 0.10).numpy()
+    assert np.abs(T - g["T_3dmatch"]).max() < 1e-5
+    g = load("ransac")
+    T, n, h, valid = TR.ransac(torch.from_numpy(g["ss"]), torch.from_numpy(g["tt"]), g["samples"], float(g["dist_th"]), float(g["similar_th"]))
+    assert h == int(g["best_h"]) and n == int(g["best_count"]) and valid == int((g["counts"] >= 0).sum())
+    assert np.abs(T.numpy() - g["T_best"]).max() < 1e-5

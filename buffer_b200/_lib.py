@@ -22,7 +22,8 @@ SIGNATURES = {
     "bfr_mutual_nn_packed": (_i, [_vp, _sz, _i, _i, _i, _vp, _vp]),
     "bfr_mutual_select": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "bfr_gather_corr": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
-    "bfr_ransac_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _u32, _u32, _f, _f, _f, _i, _vp, _vp, _vp]),
+    "bfr_ransac_workspace_bytes": (_sz, []),
+    "bfr_ransac_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _u32, _u32, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "bfr_ransac_finalize_batched": (_i, [_vp, _vp, _vp, _i, _u64, _u32, _f, _f, _vp, _vp, _vp, _vp, _vp]),
     "bfr_lrf_hypotheses": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "bfr_score_workspace_bytes": (_sz, [_i]),

@@ -24,6 +24,7 @@ from . import _lib
 DESC_DIM = 32
 _workspaces = {}
 K1_FP32, K1_TENSOR_FILTER = 0, 1
+RANSAC_FP32, RANSAC_TENSOR_FILTER = 0, 1
 
 
 def set_k1_algo(algo):
@@ -34,6 +35,17 @@ def set_k1_algo(algo):
 
 def get_k1_algo():
     return _lib.lib().bfr_config_get(1)
+
+
+def set_ransac_scoring(algo):
+    """select how RANSAC scores hypotheses on pairs of up to 5120 correspondences: RANSAC_FP32 (every residual in FP32) or
+    RANSAC_TENSOR_FILTER (tcgen05 residual filter on f16 operand splits + exact FP32 re-check of borderline residuals, the default);
+    outputs are bit-identical"""
+    _lib.check(_lib.lib().bfr_config_set(2, int(algo)), "bfr_config_set")
+
+
+def get_ransac_scoring():
+    return _lib.lib().bfr_config_get(2)
 
 
 def _stream(device=None):
@@ -190,9 +202,11 @@ def ransac_batched(corr, corr_off, corr_cnt, hypotheses, dist_th, similar_th, se
         best_packed = torch.zeros(P, dtype=torch.int64, device=corr.device)
     if splits is None:
         splits = _default_splits(P)
+    need = _lib.lib().bfr_ransac_workspace_bytes()
+    ws = _ws(need, corr.device, "ransac")
     _lib.check(_lib.lib().bfr_ransac_batched(corr.data_ptr(), corr_off.data_ptr(), corr_cnt.data_ptr(), P, int(seed), int(pair_id_base),
                                              int(h_begin), int(h_end), float(dist_th), float(similar_th), float(confidence), int(splits),
-                                             best_packed.data_ptr(), _ptr(valid_count), _stream()), "bfr_ransac_batched")
+                                             best_packed.data_ptr(), _ptr(valid_count), ws.data_ptr(), ws.numel(), _stream()), "bfr_ransac_batched")
     return best_packed
 
 

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libbuffer_b200.so")
 SOURCES = ["mutual_nn.cu", "mutual_nn_tc.cu", "ransac.cu", "refine.cu", "extras.cu", "api.cu"]
-HEADERS = ["bfr_common.cuh", "bfr_kernels.h", os.path.join("..", "..", "include", "buffer_b200.h")]
+HEADERS = ["bfr_common.cuh", "bfr_kernels.h", "bfr_tcgen05.cuh", os.path.join("..", "..", "include", "buffer_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "--fmad=false",            # no implicit contraction: every FMA in the kernels is an explicit intrinsic

@@ -19,11 +19,12 @@ __global__ void uniform_offsets_kernel(int32_t* off_m, int32_t* off_n, int P, in
 
 // carve-up of the bfr_register_batched workspace
 struct RegWs {
-    void* k1; float* corr; unsigned long long* best; float* T0;
+    void* k1; float* corr; unsigned long long* best; float* T0; void* rs;
 };
 inline size_t reg_ws_bytes(int P, int max_M, int max_N, int total_M)
 {
-    return up256(k1_workspace_bytes(P, max_M, max_N)) + up256((size_t)(total_M > 0 ? total_M : 1) * 32) + up256((size_t)P * 8) + up256((size_t)P * 64) + 256;
+    return up256(k1_workspace_bytes(P, max_M, max_N)) + up256((size_t)(total_M > 0 ? total_M : 1) * 32) + up256((size_t)P * 8) + up256((size_t)P * 64) +
+           up256(ransac_scratch_bytes()) + 256;
 }
 inline RegWs reg_ws_carve(void* ws, int P, int max_M, int max_N, int total_M)
 {
@@ -32,7 +33,8 @@ inline RegWs reg_ws_carve(void* ws, int P, int max_M, int max_N, int total_M)
     r.k1 = w; w += up256(k1_workspace_bytes(P, max_M, max_N));
     r.corr = reinterpret_cast<float*>(w); w += up256((size_t)(total_M > 0 ? total_M : 1) * 32);
     r.best = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)P * 8);
-    r.T0 = reinterpret_cast<float*>(w);
+    r.T0 = reinterpret_cast<float*>(w); w += up256((size_t)P * 64);
+    r.rs = w;
     return r;
 }
 
@@ -122,16 +124,19 @@ int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s
     return cu(gather_corr_launch(src_xyz, tgt_xyz, s_ids, t_ids, K, corr_xyz, st(stream)));
 }
 
+size_t bfr_ransac_workspace_bytes(void) { return ransac_scratch_bytes(); }
+
 int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
                        uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
-                       float dist_th, float similar_th, float confidence, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream)
+                       float dist_th, float similar_th, float confidence, int splits, uint64_t* best_packed, int32_t* valid_count,
+                       void* ws, size_t ws_bytes, void* stream)
 {
     if (P == 0) return BFR_OK;
     if (!corr_xyz || !corr_off || !corr_cnt || !best_packed) return BFR_E_NULL;
     if (P < 0 || P > BFR_MAX_PAIRS || h_end < h_begin) return BFR_E_SIZE;
     if (!aligned16(corr_xyz)) return BFR_E_ALIGN;
     return cu(ransac_launch(corr_xyz, corr_off, corr_cnt, P, seed, pair_id_base, h_begin, h_end, dist_th, similar_th, confidence, splits,
-                            reinterpret_cast<unsigned long long*>(best_packed), valid_count, st(stream)));
+                            reinterpret_cast<unsigned long long*>(best_packed), valid_count, ws, ws ? ws_bytes : 0, st(stream)));
 }
 
 int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
@@ -169,12 +174,13 @@ int bfr_score_hypotheses(const float* R, const float* t, int H, const float* src
 }
 
 namespace {
-struct VoteWs { unsigned long long* vote_best; unsigned long long* best; int32_t* sub_cnt; float* T0; float* sub_corr; };
+struct VoteWs { unsigned long long* vote_best; unsigned long long* best; int32_t* sub_cnt; float* T0; float* sub_corr; void* rs; };
 inline size_t vote_ws_bytes(int P, int total_rows)
 {
-    return 2 * up256((size_t)P * 8) + up256((size_t)P * 4) + up256((size_t)P * 64) + up256((size_t)(total_rows > 0 ? total_rows : 1) * 32) + 256;
+    return 2 * up256((size_t)P * 8) + up256((size_t)P * 4) + up256((size_t)P * 64) + up256((size_t)(total_rows > 0 ? total_rows : 1) * 32) +
+           (total_rows > 0 ? up256(ransac_scratch_bytes()) : 0) + 256;
 }
-inline VoteWs vote_ws_carve(void* ws, int P)
+inline VoteWs vote_ws_carve(void* ws, int P, int total_rows = 0)
 {
     unsigned char* w = reinterpret_cast<unsigned char*>(up256((size_t)(uintptr_t)ws));
     VoteWs v;
@@ -182,7 +188,8 @@ inline VoteWs vote_ws_carve(void* ws, int P)
     v.best = reinterpret_cast<unsigned long long*>(w); w += up256((size_t)P * 8);
     v.sub_cnt = reinterpret_cast<int32_t*>(w); w += up256((size_t)P * 4);
     v.T0 = reinterpret_cast<float*>(w); w += up256((size_t)P * 64);
-    v.sub_corr = reinterpret_cast<float*>(w);
+    v.sub_corr = reinterpret_cast<float*>(w); w += up256((size_t)(total_rows > 0 ? total_rows : 1) * 32);
+    v.rs = total_rows > 0 ? w : nullptr;
     return v;
 }
 }  // namespace
@@ -216,7 +223,7 @@ int bfr_pose_from_votes_batched(float* corr_xyz, const int32_t* corr_off, const 
     if (!aligned16(corr_xyz)) return BFR_E_ALIGN;
     if (ws_bytes < vote_ws_bytes(P, total_rows)) return BFR_E_WORKSPACE;
     cudaStream_t s = st(stream);
-    VoteWs v = vote_ws_carve(ws, P);
+    VoteWs v = vote_ws_carve(ws, P, total_rows);
     int32_t* sub_cnt = n_vote_inliers ? n_vote_inliers : v.sub_cnt;
     cudaError_t e = cudaMemsetAsync(v.best, 0, (size_t)P * 8, s);
     if (e != cudaSuccess) return (int)e;
@@ -224,7 +231,8 @@ int bfr_pose_from_votes_batched(float* corr_xyz, const int32_t* corr_off, const 
     e = lrf_vote_launch(corr_xyz, corr_off, corr_cnt, P, max_count, ind, ss_R, tt_R, azi_n, inlier_th, nullptr, v.vote_best, v.sub_corr, sub_cnt, nullptr, nullptr, s);
     if (e != cudaSuccess) return (int)e;
     // ... :313-326: RANSAC on that subset ...
-    e = ransac_launch(v.sub_corr, corr_off, sub_cnt, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, confidence, ransac_splits, v.best, nullptr, s);
+    e = ransac_launch(v.sub_corr, corr_off, sub_cnt, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, confidence, ransac_splits, v.best, nullptr,
+                      v.rs, v.rs ? ransac_scratch_bytes() : 0, s);
     if (e != cudaSuccess) return (int)e;
     float* T_ransac = refine_iters > 0 ? v.T0 : T_out;
     e = ransac_finalize_launch(v.sub_corr, corr_off, sub_cnt, P, seed, pair_id_base, dist_th, similar_th, v.best, T_ransac, n_inliers, nullptr, s);
@@ -278,7 +286,8 @@ int bfr_register_batched(const float* src_des, const float* src_xyz, const int32
     e = k1_launch(src_des, tgt_des, src_off, tgt_off, P, max_M, max_N, total_M, total_N, D, 1, w.k1, nullptr, nullptr, nullptr, nullptr,
                   src_xyz, tgt_xyz, nullptr, nullptr, n_mutual, w.corr, s);
     if (e != cudaSuccess) return (int)e;
-    e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, confidence, ransac_splits, w.best, nullptr, s);
+    e = ransac_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, 0u, (uint32_t)hypotheses, dist_th, similar_th, confidence, ransac_splits, w.best, nullptr,
+                      w.rs, ransac_scratch_bytes(), s);
     if (e != cudaSuccess) return (int)e;
     float* T_ransac = refine_iters > 0 ? w.T0 : T_out;
     e = ransac_finalize_launch(w.corr, src_off, n_mutual, P, seed, pair_id_base, dist_th, similar_th, w.best, T_ransac, n_inliers, nullptr, s);
@@ -392,12 +401,14 @@ int bfr_svd3_batched(const float* x, int B, float* u, float* s, float* v, void* 
 int bfr_config_set(int key, int value)
 {
     if (key == BFR_CFG_K1_ALGO) { if (value != 0 && value != 1) return BFR_E_SIZE; k1_set_algo(value); return BFR_OK; }
+    if (key == BFR_CFG_RANSAC_TC) { if (value != 0 && value != 1) return BFR_E_SIZE; ransac_set_tc(value); return BFR_OK; }
     return BFR_E_SIZE;
 }
 
 int bfr_config_get(int key)
 {
     if (key == BFR_CFG_K1_ALGO) return k1_get_algo();
+    if (key == BFR_CFG_RANSAC_TC) return ransac_get_tc();
     return BFR_E_SIZE;
 }
 

@@ -36,7 +36,10 @@ void k1_set_events(cudaEvent_t e0, cudaEvent_t e1);
 // K2 + K3 (ransac.cu)
 cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
                           uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, float confidence, int splits,
-                          unsigned long long* best_packed, int32_t* valid_count, cudaStream_t stream);
+                          unsigned long long* best_packed, int32_t* valid_count, void* tc_scratch, size_t tc_scratch_bytes, cudaStream_t stream);
+size_t ransac_scratch_bytes();
+void ransac_set_tc(int on);
+int ransac_get_tc();
 cudaError_t lrf_vote_launch(float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, int max_count, const float* ind, const float* ss_R, const float* tt_R,
                             float azi_n, float inlier_th, int32_t* counts, unsigned long long* vote_best, float* sub_corr, int32_t* sub_cnt,
                             int64_t* best_idx, int64_t* inlier_ind, cudaStream_t stream);

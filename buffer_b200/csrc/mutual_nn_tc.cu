@@ -27,6 +27,7 @@
 // -DTC_TIMING adds clock64 phase timers and event counters (tools/k1_bench.py prints them); it is never defined in the product build.
 #include "bfr_common.cuh"
 #include "bfr_kernels.h"
+#include "bfr_tcgen05.cuh"
 #include <cuda.h>
 #include <atomic>
 #include <cmath>
@@ -102,48 +103,6 @@ BFR_DEVINL uint64_t umma_desc_sw64(const void* smem)
 {   // K-major, SWIZZLE_64B: 8-row groups 512 B apart (SBO = 32 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell), layout 4 = SW64
     return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
-BFR_DEVINL void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-BFR_DEVINL void umma_commit(uint64_t* bar) { asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
-BFR_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-BFR_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// issue only; the registers become valid after tmem_ld_wait()
-BFR_DEVINL void tmem_ld32_issue(uint32_t taddr, float (&v)[32])
-{
-    uint32_t r[32];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
-                   "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
-                   "=r"(r[30]), "=r"(r[31])
-                 : "r"(taddr));
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-// wait for all outstanding tcgen05.ld of this thread; the buffer is threaded through as in/out so that no use is hoisted above
-BFR_DEVINL void tmem_ld_wait(float (&v)[32])
-{
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
-                   "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]),
-                   "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
-                 :: "memory");
-}
-
-// no instruction: orders the uses of a second in-flight buffer after the tcgen05.wait::ld issued just before (volatile asm keeps program order)
-BFR_DEVINL void tmem_ld_pin(float (&v)[32])
-{
-    asm volatile(""
-                 : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]), "+f"(v[9]), "+f"(v[10]),
-                   "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15]), "+f"(v[16]), "+f"(v[17]), "+f"(v[18]), "+f"(v[19]), "+f"(v[20]),
-                   "+f"(v[21]), "+f"(v[22]), "+f"(v[23]), "+f"(v[24]), "+f"(v[25]), "+f"(v[26]), "+f"(v[27]), "+f"(v[28]), "+f"(v[29]), "+f"(v[30]), "+f"(v[31])
-                 :: "memory");
-}
-
 // exact score of (own row, candidate row) — the oracle's chain.  COLDIR = the "own" side is the target set.
 BFR_DEVINL float exact_score(bool COLDIR, const float4 (&own)[8], float own_hn, const float* __restrict__ cand_row, float cand_hn)
 {

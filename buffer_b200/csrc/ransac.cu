@@ -5,55 +5,106 @@
 // scoring block (models/BUFFER.py:303-311).  Semantics and exact arithmetic: oracle/bfr_oracle.c (orc_hypothesis,
 // orc_count_inliers, orc_ransac, orc_score_hypotheses, orc_lrf_vote); DESIGN.md §K2/§K3.
 //
-// ransac_kernel: persistent CTAs (512 threads, one per SM) walk work items = (pair, slice of the hypothesis range) round-robin.
-// A pair's correspondences (up to RS_CHUNK = 5120, 24 bytes each: 120 KB) are loaded ONCE per item into shared memory in a
-// pair-interleaved layout and serve both the random sample gathers of stage 1 and the scoring loop; larger pairs stream through the
-// same buffer in chunks and gather their samples from global memory.  Per round every thread draws RS_S1 hypotheses (Philox counter
-// = (h, pair_id, 0, 0)) and runs the cheap checks (repeated index, edge lengths); survivors (~10 %) are compacted into queue 1 so that
-// the 3-point Kabsch + distance check runs on dense warps; what passes (a few %) goes to queue 2.  Whenever queue 2 holds a full block's
-// worth, each thread takes one hypothesis and scores it against ALL correspondences: FFMA2 over two correspondences per instruction with
-// warp-uniform LDS.128 broadcasts.  The inlier count never leaves the thread; a CTA's best (count << 32 | ~h) goes out with one 64-bit
-// atomicMax per item.
+// ransac_kernel: persistent CTAs (512 threads, one per SM) walk work items = (pair, slice of the
+// hypothesis range) round-robin.  A pair's correspondences (up to RS_CHUNK = 5120, 24 bytes each: 120 KB) are loaded ONCE per item into
+// shared memory in a pair-interleaved layout and serve the random sample gathers of stage 1, the fits and the exact scoring loop; larger
+// pairs stream through the same buffer in chunks and gather their samples from global memory.  Per round every thread draws RS_S1
+// hypotheses (Philox counter = (h, pair_id, 0, 0)) and runs the cheap checks (repeated index, edge lengths); survivors (~10 %) are
+// compacted into queue 1 so that the 3-point Kabsch + distance check runs on dense warps; what passes (a few %) goes to queue 2.
+//
+// Scoring (inlier count of every queued hypothesis over ALL correspondences of the pair) has two implementations with identical results:
+//  * exact FP32 (score_queue): each thread takes one hypothesis; FFMA2 over two correspondences per instruction with warp-uniform
+//    LDS.128 broadcasts; ~11 instructions per (hypothesis, correspondence).
+//  * tensor-core filter (tc_flush, the default for shared-memory-resident pairs when the caller passes scratch memory): the residual
+//    components x_i(h,c) = sum_j R_ij s_j + t_i - q_i are bilinear in (R_i, t_i | 1) and (s, 1, q), so a 128-correspondence x
+//    80-hypothesis block of all three components is ONE 128 x 256 accumulator tile of two K = 16 tcgen05.mma kind::f16 on 2-level f16
+//    splits of the FP32 operands (relative operand error 2^-24).  The epilogue (thread = correspondence, TMEM -> registers) needs three
+//    FMAs, a sign-bit add and a band test per (h,c); only pairs whose approximate d^2 lies within a rigorous error band of the threshold
+//    (none to a handful per pair) are re-evaluated with the oracle's FP32 chain, so the counts stay bit-exact.
+// The inlier count never leaves the CTA; a CTA's best (count << 32 | ~h) goes out with one 64-bit atomicMax per item.
 // confidence < 1 (Open3D's RANSACConvergenceCriteria, models/BUFFER.py:323-324): one item per pair, rounds of 512 hypotheses, and after
 // every round the sequential rule of Open3D (stop once iteration >= ceil(log(1-c)/log(1-fitness^3)) of the best so far) is replayed
 // in hypothesis order, so the result equals a one-thread sequential run (oracle orc_ransac_confidence) exactly.
 #include "bfr_common.cuh"
 #include "bfr_kernels.h"
+#include "bfr_tcgen05.cuh"
+#include <cuda_fp16.h>
 #include <cmath>
 
 namespace bfr {
 
-constexpr int RS_THREADS = 512;
+constexpr int RS_THREADS = 512;                 // worker threads: stage 1, fits, scoring / tensor-core epilogue
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_CHUNK = 5120;                  // correspondences per shared-memory chunk; pairs with K <= RS_CHUNK stay resident
 #ifndef RS_S1_N
 #define RS_S1_N 4
 #endif
 constexpr int RS_S1 = RS_S1_N;                     // stage-1 hypotheses per thread and round
-constexpr int RS_QCAP = 2 * RS_THREADS;            // queue 2 holds < RS_THREADS leftovers plus the survivors of one fit block
-constexpr int RS_Q1CAP = (1 + RS_S1) * RS_THREADS; // queue 1 holds < RS_THREADS leftovers plus one round's survivors
+constexpr int RS_QCAP = 2 * RS_THREADS;            // queue 2 (exact scoring): < RS_THREADS leftovers plus the survivors of one fit block
+constexpr int RS_Q1CAP = (1 + RS_S1) * RS_THREADS; // queue 1 holds < RS_THREADS leftovers plus one round's survivors (hypothesis index only)
+constexpr int RS_MAX_CTAS = 160;                   // upper bound of the persistent grid (sizes the tensor-core scratch)
 
+// tensor-core scoring filter
+constexpr int RT_HT = 40;                       // hypotheses per accumulator tile: 4 chunks of 32 TMEM columns = 5 hypothesis pairs x (x x' y y' z z') + 2 unused
+constexpr int RT_FLUSH = 2 * RT_HT;             // hypotheses per flush: two warp groups, each ping-ponging between two 128 x 128 accumulator tiles (512 TMEM columns)
+constexpr int RT_QCAP = RT_FLUSH + RS_THREADS;  // queue 2 (tensor-core scoring): < RT_FLUSH leftovers plus the survivors of one fit block
+constexpr int RT_TILE = 128;                    // correspondences per A tile (MMA M)
+constexpr int RT_TILE_BYTES = RT_TILE * 32;     // K = 16 f16 per row
+constexpr int RT_STAGES = 8;                    // A tiles in flight (TMA ring): the MMAs run two tiles ahead of the epilogue, the copies five more
+constexpr int RT_MAX_TILES = RS_CHUNK / RT_TILE;
+constexpr float RT_RANGE = 8192.0f;             // largest |s|_1, |q_i|, |t_i| the f16 splits are used for (beyond: exact FP32 scoring)
+constexpr float RT_PAD_Q = 32768.0f;            // target coordinate of the padding rows of the last A tile: never an inlier, never in the band
+
+#ifdef RS_TRACE
+constexpr int RTR_EV = 8, RTR_TILES = 20;
+__device__ unsigned int g_trace[16 * RTR_EV * RTR_TILES];      // clocks of lane 0 of every warp of CTA 0 during one flush: [warp][tile][event]
+#define RTR(ev, tile) { if (trace_on && lane == 0 && (tile) < RTR_TILES) sm.trace[warp][(tile) * RTR_EV + (ev)] = (unsigned)clock64(); }
+#else
+#define RTR(ev, tile) { }
+#endif
 #ifdef RS_TIMING
 __device__ unsigned long long g_rs_dbg[8];
+__device__ unsigned long long g_rt_dbg2[8];     // issue path: a_empty wait + TMA issue, a_full wait + MMA issue, issues; thread 0: pure tcgen05.ld, hand-back
+__device__ unsigned long long g_rt_dbg[8];      // tc_flush, summed over thread 0 of every CTA: build, wait acc_full, tcgen05.ld, math + issue, reduce, flushes, tiles
 #define RST(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
 #else
 #define RST(acc, stmt) { stmt; }
 #endif
 
-struct __align__(16) RsSmem {
+struct __align__(1024) RsSmem {
     float4 chunk[RS_CHUNK / 2][3];              // per pair of correspondences: (sx sx' sy sy')(sz sz' qx qx')(qy qy' qz qz')
-    float q[12][RS_QCAP];                       // queue 2: hypotheses that passed every check: R (9) + t (3), SoA
-    uint32_t qh[RS_QCAP];
-    uint4 q1[RS_Q1CAP];                         // queue 1: survivors of the cheap checks: {h, i0, i1, i2}; idle: partial counts / round results
+    union {
+        struct {                                // exact scoring
+            float q[12][RS_QCAP];               // queue 2: hypotheses that passed every check: R (9) + t (3), SoA
+            uint32_t qh[RS_QCAP];
+        } ex;
+        struct {                                // tensor-core scoring
+            unsigned char a_ring[RT_STAGES][RT_TILE_BYTES];   // A tiles: 128 correspondences x 16 f16, unswizzled K-major core matrices
+            unsigned char b_op[2][2][128 * 32];               // [warp group][B1 | B2]: 128 (hypothesis, component) rows x 16 f16
+            float q[12][RT_QCAP];
+            uint32_t qh[RT_QCAP];
+            int cnt[RT_FLUSH];                                // inlier counts of the hypotheses of the current flush
+        } tc;
+    } u;
+    uint32_t q1[RS_Q1CAP];                      // queue 1: survivors of the cheap checks (hypothesis index); idle: partial counts / round results
     unsigned long long red[RS_WARPS];
+    uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_full[2][2];     // acc_full[warp group][accumulator buffer]
+    uint32_t acc_arrivals[2][2];                // epilogue warps that have pulled the buffer's tile out of TMEM (the 8th issues the MMAs of the tile after next)
     unsigned long long seq_best;                // confidence mode: state of the sequential replay
     uint32_t seq_bound;
     int seq_stop;
     int q1count;
     int qcount;
+    uint32_t tmem_base;
+#ifdef RS_TRACE
+    unsigned int trace[16][8 * 20];
+#endif
+    uint32_t stat[4];                           // float bits: max |s|_1, max |q_i| of the pair, max |t_i| of the flush; [3] != 0: out of range / non-finite
 };
-static_assert(sizeof(RsSmem) <= 227 * 1024, "RsSmem must fit one CTA's shared memory");
-static_assert(RS_Q1CAP * 4 >= 5 * RS_THREADS, "queue 1 doubles as partial counts + round results of the confidence mode");
+static_assert(sizeof(RsSmem) + 1024 <= 227 * 1024, "RsSmem must fit one CTA's shared memory");
+static_assert(RS_Q1CAP >= 5 * RS_THREADS, "queue 1 doubles as partial counts + round results of the confidence mode");
+static_assert(RT_TILE_BYTES >= 2 * RS_THREADS * (int)sizeof(int), "an A-ring stage doubles as scratch of the exact fallback of a flush");
+static_assert(offsetof(RsSmem, u) % 1024 == 0, "operand tiles start on a 1 KB boundary");
 
 // a4 / LRF-vote scoring keeps the smaller 256-thread shape (per-correspondence thresholds in a 4th float4)
 constexpr int SC_THREADS = 256;
@@ -62,6 +113,8 @@ struct __align__(16) ScSmem {
     float4 chunk[SC_CHUNK / 2][4];              // ... + (w w' - -): per-correspondence squared-distance thresholds
     unsigned long long red[SC_THREADS / 32];
 };
+
+BFR_DEVINL void rs_sync() { __syncthreads(); }
 
 // cooperative load of correspondences [c0, c0 + CHUNK) of one pair (8-float records) into the pair-interleaved layout
 template <int NF, int CHUNK, int THREADS>
@@ -119,19 +172,22 @@ BFR_DEVINL int score_pairs(const float4 (*chunk)[NF], int g_begin, int g_end, co
     return count;
 }
 
-// minimal-sample gather from the resident chunk: record c lives in pair g = c / 2, slot c % 2
+// one record of the resident chunk: record c lives in pair g = c / 2, slot c % 2
+BFR_DEVINL void load_record_smem(const RsSmem& sm, uint32_t c, float s[3], float q[3])
+{
+    const float* f = reinterpret_cast<const float*>(&sm.chunk[c >> 1][0]) + (c & 1u);
+    s[0] = f[0]; s[1] = f[2]; s[2] = f[4]; q[0] = f[6]; q[1] = f[8]; q[2] = f[10];
+}
 BFR_DEVINL void load_sample_smem(const RsSmem& sm, const uint32_t id[3], float s[3][3], float q[3][3])
 {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const float* f = reinterpret_cast<const float*>(&sm.chunk[id[i] >> 1][0]) + (id[i] & 1u);
-        s[i][0] = f[0]; s[i][1] = f[2]; s[i][2] = f[4]; q[i][0] = f[6]; q[i][1] = f[8]; q[i][2] = f[10];
-    }
+    for (int i = 0; i < 3; ++i) load_record_smem(sm, id[i], s[i], q[i]);
 }
 
 template <bool RES>
-BFR_DEVINL bool precheck(const RsSmem& sm, const float4* __restrict__ corr_p, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h, float sim2, uint32_t id[3])
+BFR_DEVINL bool precheck(const RsSmem& sm, const float4* __restrict__ corr_p, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h, float sim2)
 {
+    uint32_t id[3];
     sample3(seed, pair_id, h, K, id);
     if (id[0] == id[1] || id[0] == id[2] || id[1] == id[2]) return false;
     float s[3][3], q[3][3];
@@ -139,61 +195,395 @@ BFR_DEVINL bool precheck(const RsSmem& sm, const float4* __restrict__ corr_p, ui
     return edge_lengths_ok(s, q, sim2);
 }
 
-// score `n` queued hypotheses against all K correspondences.  A full queue (n = RS_THREADS) gives every thread one hypothesis.  A partial
-// flush (n < RS_THREADS) would leave most warps idle, so the nw = ceil(n / 32) warps' worth of hypotheses are replicated over the
-// RS_WARPS / nw groups of warps and every group scores its own slice of each chunk (the loads stay warp-uniform broadcasts); the partial
-// counts are integer sums, so the total is exact whatever the split.  Returns true in the thread that owns queue entry hi (index h, count).
-template <bool RES>
-BFR_DEVINL bool score_queue(RsSmem& sm, const float4* __restrict__ corr, int K, int n, float d2max, uint32_t& h, int& count, int& hi)
+template <bool TC> BFR_DEVINL float& q2(RsSmem& sm, int k, int i) { if (TC) return sm.u.tc.q[k][i]; else return sm.u.ex.q[k][i]; }
+template <bool TC> BFR_DEVINL uint32_t& q2h(RsSmem& sm, int i) { if (TC) return sm.u.tc.qh[i]; else return sm.u.ex.qh[i]; }
+
+// exact FP32 scoring of the `n` queued hypotheses [base, base + n) against all K correspondences.  A full block (n = RS_THREADS) gives
+// every thread one hypothesis.  With n < RS_THREADS most warps would idle, so the nw = ceil(n / 32) warps' worth of hypotheses are
+// replicated over the RS_WARPS / nw groups of warps and every group scores its own slice of each chunk (the loads stay warp-uniform
+// broadcasts); the partial counts are integer sums, so the total is exact whatever the split.  Returns true in the thread that owns queue
+// entry base + hi (index h, count).  `partial`: RS_THREADS ints of scratch (only touched when n < RS_THREADS).
+template <bool RES, bool TC>
+BFR_DEVINL bool score_queue(RsSmem& sm, const float4* __restrict__ corr, int K, int base, int n, float d2max, int* partial, uint32_t& h, int& count, int& hi)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nw = (n + 31) >> 5;                                     // warps that hold hypotheses
     const int nparts = RS_WARPS / nw;                                 // correspondence slices (1 for a full queue)
     const int part = warp / nw;
-    hi = (warp % nw) * 32 + lane;                                     // this thread: hypothesis hi of the queue, slice `part`
+    hi = (warp % nw) * 32 + lane;                                     // this thread: hypothesis hi of the block, slice `part`
     const bool warp_has_work = part < nparts;
     const bool mine = warp_has_work && hi < n;
     float R[9] = { 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f }, t[3] = { 0.f, 0.f, 0.f };
     h = 0;
     if (mine) {
 #pragma unroll
-        for (int k = 0; k < 9; ++k) R[k] = sm.q[k][hi];
+        for (int k = 0; k < 9; ++k) R[k] = q2<TC>(sm, k, base + hi);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) t[k] = sm.q[9 + k][hi];
-        h = sm.qh[hi];
+        for (int k = 0; k < 3; ++k) t[k] = q2<TC>(sm, 9 + k, base + hi);
+        h = q2h<TC>(sm, base + hi);
     }
-    int* partial = reinterpret_cast<int*>(sm.q1);                     // queue 1 is empty whenever a partial flush runs
-    if (nparts > 1) { partial[threadIdx.x] = 0; __syncthreads(); }
+    if (nparts > 1) { partial[threadIdx.x] = 0; rs_sync(); }
     count = 0;
     for (int c0 = 0; c0 < K; c0 += RS_CHUNK) {
         if (!RES) {
-            __syncthreads();                   // previous chunk fully consumed
+            rs_sync();                         // previous chunk fully consumed
             load_chunk<3, RS_CHUNK, RS_THREADS>(sm.chunk, corr, K, c0);
-            __syncthreads();
+            rs_sync();
         }
         const int npairs = (min(RS_CHUNK, K - c0) + 1) >> 1;
         if (warp_has_work) count += score_pairs<3, false>(sm.chunk, (part * npairs) / nparts, ((part + 1) * npairs) / nparts, R, t, d2max);
     }
     if (nparts > 1) {
         if (mine) atomicAdd(&partial[hi], count);
-        __syncthreads();
+        rs_sync();
         count = partial[hi < RS_THREADS ? hi : 0];
-        __syncthreads();                       // partial[] (= queue 1) may be refilled after this
+        rs_sync();                             // partial[] (= queue 1) may be refilled after this
     }
     return mine && part == 0;
 }
 
+BFR_DEVINL unsigned long long pack_count(int count, uint32_t h) { return ((unsigned long long)(uint32_t)count << 32) | (unsigned long long)(0xFFFFFFFFu - h); }
+
+// ---- tensor-core scoring filter ----------------------------------------------------------------------------------------------------
+// Operand rows (16 f16 = 32 bytes, K-major, unswizzled: 8 x 16-byte core matrices, the two K halves 128 B apart, 8-row groups 256 B apart):
+//   A row of correspondence c:        [s_hi(3) s_lo(3) 1 q_hi(3) q_lo(3) 0 0 0]                    hi = rn_f16(v), lo = rn_f16(v - hi)
+//   B1 row of (hypothesis h, comp i): [R_i,hi(3) R_i,hi(3) t_i,hi -e_i(3) -e_i(3) 0 0 0]
+//   B2 row:                           [R_i,lo(3) 0 0 0 t_i,lo 0 ...]
+// A B1^T + A B2^T = x_i(h,c) up to |error| <= 3 * 2^-24 * B' from the splits (B' = sum_j |R_ij s_j| + |t_i| + |q_i|) plus the
+// accumulation error of the tensor core (measured: total 2^-21.6 B', tools/microbench/rs_mma.cu; budgeted here: 2^-19 B').
+BFR_DEVINL uint32_t rt_row_offset(int r) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 16); }     // first 16-byte half; the second is + 128
+BFR_DEVINL uint64_t rt_desc(const void* smem)
+{   // LBO = 128 B (K direction), SBO = 256 B (row groups), descriptor version 1, no swizzle
+    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+}
+BFR_DEVINL void split_f16(float v, __half& hi, __half& lo)
+{
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(__fsub_rn(v, __half2float(hi)));
+}
+BFR_DEVINL uint32_t pack_h2(__half lo16, __half hi16) { return (uint32_t)__half_as_ushort(lo16) | ((uint32_t)__half_as_ushort(hi16) << 16); }
+BFR_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+BFR_DEVINL float min3abs(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c))); return d; }
+
+// Once per item: the pair's A tiles (f16 splits of every resident correspondence, padded to whole tiles) go to this CTA's scratch in
+// global memory (it stays in L2; the tensor-core warp streams it back tile by tile with 1-D TMA copies, once per flush), and the
+// pair's magnitude bounds are reduced.  Returns false if the pair must be scored exactly (coordinates out of range / non-finite).
+BFR_DEVINL bool tc_prepare_pair(RsSmem& sm, int K, unsigned char* __restrict__ scratch, float& s1max, float& qmax)
+{
+    if (threadIdx.x < 4) sm.stat[threadIdx.x] = 0u;
+    rs_sync();
+    const int ntiles = (K + RT_TILE - 1) / RT_TILE;
+    float s1 = 0.0f, qm = 0.0f; bool bad = false;
+    const __half one = __float2half_rn(1.0f), zero = __float2half_rn(0.0f);
+    for (int c = threadIdx.x; c < ntiles * RT_TILE; c += RS_THREADS) {
+        float s[3] = { 0.f, 0.f, 0.f }, q[3] = { RT_PAD_Q, RT_PAD_Q, RT_PAD_Q };
+        if (c < K) {
+            load_record_smem(sm, (uint32_t)c, s, q);
+            const float a = fabsf(s[0]) + fabsf(s[1]) + fabsf(s[2]), b = fmaxf(fmaxf(fabsf(q[0]), fabsf(q[1])), fabsf(q[2]));
+            bad |= !(a <= RT_RANGE) || !(fabsf(q[0]) <= RT_RANGE) || !(fabsf(q[1]) <= RT_RANGE) || !(fabsf(q[2]) <= RT_RANGE);
+            s1 = fmaxf(s1, a); qm = fmaxf(qm, b);
+        }
+        __half sh[3], sl[3], qh[3], ql[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { split_f16(s[k], sh[k], sl[k]); split_f16(q[k], qh[k], ql[k]); }
+        const uint4 c0 = make_uint4(pack_h2(sh[0], sh[1]), pack_h2(sh[2], sl[0]), pack_h2(sl[1], sl[2]), pack_h2(one, qh[0]));
+        const uint4 c1 = make_uint4(pack_h2(qh[1], qh[2]), pack_h2(ql[0], ql[1]), pack_h2(ql[2], zero), 0u);
+        unsigned char* dst = scratch + (size_t)(c >> 7) * RT_TILE_BYTES + rt_row_offset(c & (RT_TILE - 1));
+        *reinterpret_cast<uint4*>(dst) = c0;
+        *reinterpret_cast<uint4*>(dst + 128) = c1;
+    }
+    s1 = warp_max(s1); qm = warp_max(qm);
+    bad = __any_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(&sm.stat[0], __float_as_uint(s1)); atomicMax(&sm.stat[1], __float_as_uint(qm));      // non-negative floats order like their bits
+        if (bad) sm.stat[3] = 1u;
+    }
+    __threadfence();
+    fence_proxy_async_all();                    // the scratch is read by the async proxy (TMA)
+    rs_sync();
+    s1max = __uint_as_float(sm.stat[0]); qmax = __uint_as_float(sm.stat[1]);
+    return sm.stat[3] == 0u;
+}
+
+// Feeding the tensor core (single threads of the epilogue warps; there is no dedicated warp: 17 warps would cut the register budget
+// to 96).  Tile numbers `g` run on across flushes and items, so every mbarrier just keeps flipping phases.
+//  * rt_load_tile: 1-D TMA copy of A tile i of the item into its ring stage, once both groups' MMAs on the stage's previous occupant
+//    have completed (a_empty: two tcgen05.commit arrivals per use).
+//  * rt_issue_tile: the two MMAs of an A tile into one accumulator buffer (B1 then B2 accumulate), commit -> acc_full and a_empty.  It
+//    sits on the critical path buffer handed back -> buffer full again, so everything is precomputed: the caller passes the low words of
+//    the three shared-memory descriptors (the high word is the same for all) and the two barrier addresses.
+BFR_DEVINL void rt_load_tile(RsSmem& sm, const unsigned char* __restrict__ scratch, uint32_t g, int i)
+{
+    const int s = (int)(g % RT_STAGES);
+    mbar_wait(&sm.a_empty[s], ((g / RT_STAGES) & 1u) ^ 1u);
+    mbar_expect_tx(&sm.a_full[s], RT_TILE_BYTES);
+    tma_load_1d(sm.u.tc.a_ring[s], scratch + (size_t)i * RT_TILE_BYTES, RT_TILE_BYTES, &sm.a_full[s]);
+}
+constexpr uint32_t RT_DESC_HI = 16u | (1u << 14);                    // SBO = 256 B (8-row groups), descriptor version 1, no swizzle
+BFR_DEVINL uint32_t rt_desc_lo(const void* smem) { return ((smem_u32(smem) >> 4) & 0x3FFFu) | (8u << 16); }     // LBO = 128 B (K direction)
+BFR_DEVINL void rt_issue_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t b1_lo, uint32_t b2_lo, uint32_t bar_acc_full, uint32_t bar_a_empty)
+{
+    // instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 128, M = 128
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    asm volatile("{\n\t.reg .b64 da, db1, db2;\n\t.reg .pred pt, pf;\n\t"
+                 "mov.b64 da, {%1, %4};\n\tmov.b64 db1, {%2, %4};\n\tmov.b64 db2, {%3, %4};\n\t"
+                 "setp.eq.u32 pt, %0, %0;\n\tsetp.ne.u32 pf, %0, %0;\n\t"
+                 "tcgen05.fence::after_thread_sync;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db1, %5, pf;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db2, %5, pt;\n\t"
+                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
+                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b1_lo), "r"(b2_lo), "r"(RT_DESC_HI), "r"(idesc), "r"(bar_acc_full), "r"(bar_a_empty) : "memory");
+}
+static_assert(RT_STAGES == 8, "the ring index is taken with a mask");
+BFR_DEVINL uint32_t atom_inc_acq_rel(uint32_t* p)
+{
+    uint32_t old;
+#ifdef RT_ATOM_RELAXED
+    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+#else
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
+#endif
+    return old;
+}
+
+// Out of line (rare): correspondence c against the (up to) 10 hypotheses of one chunk, queue entries qbase .. qbase + 9 (the first
+// `nvalid` exist); w[k] = approximate d2 - d2max.  Every pair inside the band is re-evaluated with the oracle's FP32 chain.
+// Returns bit k: exact says inlier but the filter said no; bit 16 + k: the filter said inlier but exact says no.
+__device__ __noinline__ uint32_t tc_recheck(const RsSmem& sm, uint32_t c, int qbase, int nvalid, float d2max, float band, const float (&w)[10])
+{
+    float s[3], q[3];
+    load_record_smem(sm, c, s, q);
+    uint32_t fix = 0u;
+#pragma unroll 1
+    for (int k = 0; k < 10; ++k) {
+        const float wk = k == 0 ? w[0] : k == 1 ? w[1] : k == 2 ? w[2] : k == 3 ? w[3] : k == 4 ? w[4] : k == 5 ? w[5] : k == 6 ? w[6] : k == 7 ? w[7] : k == 8 ? w[8] : w[9];
+        if (fabsf(wk) <= band && k < nvalid) {
+            float R[9], tt[3];
+#pragma unroll
+            for (int e = 0; e < 9; ++e) R[e] = sm.u.tc.q[e][qbase + k];
+#pragma unroll
+            for (int e = 0; e < 3; ++e) tt[e] = sm.u.tc.q[9 + e][qbase + k];
+            const bool exact_in = resid2(R, tt, s[0], s[1], s[2], q[0], q[1], q[2]) < d2max;
+            const bool approx_in = (__float_as_uint(wk) >> 31) != 0u;
+            if (exact_in && !approx_in) fix |= 1u << k;
+            if (!exact_in && approx_in) fix |= 1u << (16 + k);
+        }
+    }
+    return fix;
+}
+
+// Score the queued hypotheses [base, base + n), n <= RT_FLUSH, on the tensor cores.  Warps 0-7 (group 0) own flush-local hypotheses
+// 0-39, warps 8-15 (group 1) hypotheses 40-79.  A group's 40 hypotheses x 3 components are the 128 columns of an accumulator tile (4
+// chunks of 32 columns; a chunk holds 10 hypotheses as 5 pairs (x_a x_b y_a y_b z_a z_b) so that one FFMA2 squares a component of two
+// hypotheses) and the group ping-pongs between two such tiles: while its threads work on the tile of A tile i (thread = correspondence:
+// warp w reads TMEM lanes 32 (w % 4) .., column half (w / 4) % 2), the tensor core fills the other buffer with A tile i + 1.  A warp pulls
+// its 64 columns into registers, hands the buffer back, and only then does the arithmetic; the last of the 8 warps to hand it back
+// issues the MMAs of A tile i + 2.  `tile0` = A tiles consumed before this flush (the mbarrier phase clock).
+// Returns, in threads < n, the exact inlier count of hypothesis base + threadIdx.x; bit 30 is set (in every thread) if the tensor-core path
+// ran, i.e. ceil(K / 128) A tiles were consumed.  Out of line: ransac_item flushes from three places.
+__device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d2max, float s1max, float qmax, const unsigned char* __restrict__ scratch, uint32_t tile0)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef RS_TRACE
+    const bool trace_on = blockIdx.x == 0 && tile0 >= 80u && tile0 < 120u;
+#endif
+#ifdef RS_TIMING
+    long long tq0 = clock64(), tq_wait = 0, tq_ld = 0, tq_math = 0, tq_x[3] = { 0, 0, 0 };
+#endif
+    // ---- B operands of the flush + the largest |t_i| ----
+    if (threadIdx.x < RT_FLUSH) sm.u.tc.cnt[threadIdx.x] = 0;
+    float tm = 0.0f; bool bad = false;
+    if ((int)threadIdx.x < 3 * n) {
+        const int hl = (int)threadIdx.x / 3, comp = (int)threadIdx.x - 3 * hl, qi = base + hl;
+        const float r0 = sm.u.tc.q[3 * comp][qi], r1 = sm.u.tc.q[3 * comp + 1][qi], r2 = sm.u.tc.q[3 * comp + 2][qi], tt = sm.u.tc.q[9 + comp][qi];
+        tm = fabsf(tt);
+        bad = !(tm <= RT_RANGE) || !(fabsf(r0) <= 1.001f) || !(fabsf(r1) <= 1.001f) || !(fabsf(r2) <= 1.001f);
+        __half h0, l0, h1, l1, h2, l2, ht, lt;
+        split_f16(r0, h0, l0); split_f16(r1, h1, l1); split_f16(r2, h2, l2); split_f16(tt, ht, lt);
+        const __half zero = __float2half_rn(0.0f), m1 = __float2half_rn(-1.0f);
+        const __half e0 = comp == 0 ? m1 : zero, e1 = comp == 1 ? m1 : zero, e2 = comp == 2 ? m1 : zero;
+        const int grp = hl / RT_HT, hh = hl - grp * RT_HT, ch = hh / 10, k = hh - ch * 10;
+        const int col = ch * 32 + (k >> 1) * 6 + comp * 2 + (k & 1);
+        unsigned char* b1 = sm.u.tc.b_op[grp][0] + rt_row_offset(col);
+        unsigned char* b2 = sm.u.tc.b_op[grp][1] + rt_row_offset(col);
+        *reinterpret_cast<uint4*>(b1) = make_uint4(pack_h2(h0, h1), pack_h2(h2, h0), pack_h2(h1, h2), pack_h2(ht, e0));
+        *reinterpret_cast<uint4*>(b1 + 128) = make_uint4(pack_h2(e1, e2), pack_h2(e0, e1), pack_h2(e2, zero), 0u);
+        *reinterpret_cast<uint4*>(b2) = make_uint4(pack_h2(l0, l1), pack_h2(l2, zero), 0u, pack_h2(lt, zero));
+        *reinterpret_cast<uint4*>(b2 + 128) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    tm = warp_max(tm);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) { atomicMax(&sm.stat[2], __float_as_uint(tm)); if (bad) sm.stat[3] = 1u; }
+    fence_proxy_async();                        // the operand rows are read by the async proxy (tcgen05.mma)
+    rs_sync();
+    const float tmax = __uint_as_float(sm.stat[2]);
+    const bool fallback = sm.stat[3] != 0u;
+    // |x~ - x_oracle| <= delta = (2^-19 + 2^-22) B' (tensor-core path + the four roundings of the FP32 chain), B' <= 1.001 |s|_1 + |t_i| + |q_i|;
+    // then |d2~ - d2_oracle| <= delta (2 sqrt(3) sqrt(d2) + 3 delta) + 2^-20 d2max as long as d2 <= 2 d2max, and beyond 2 d2max the sign of
+    // d2~ - d2max cannot flip if delta <= sqrt(d2max) / 64.  1.02: rounding of this very computation.
+    const float bp = 1.001f * s1max + tmax + qmax;
+    const float delta = 1.02f * 2.1457672e-6f * bp;
+    const float rt = sqrtf(d2max);
+    const float band = 1.02f * (delta * (4.8989795f * rt + 3.0f * delta) + 9.5367432e-7f * d2max);
+    const bool ok = !fallback && delta <= 0.015625f * rt && d2max > 0.0f && d2max <= 1.0e6f;
+    if (!ok) {                                  // block-uniform: score these hypotheses exactly
+        rs_sync();
+        if (threadIdx.x == 0) { sm.stat[2] = 0u; sm.stat[3] = 0u; }
+        uint32_t h; int count, hi;
+        int* partial = reinterpret_cast<int*>(sm.u.tc.a_ring[0]);    // the ring is idle (queue 1 may still hold entries)
+        int* res = partial + RS_THREADS;
+        const bool mine = score_queue<true, true>(sm, nullptr, K, base, n, d2max, partial, h, count, hi);
+        rs_sync();
+        if (mine) res[hi] = count;
+        rs_sync();
+        const int r = (int)threadIdx.x < n ? res[threadIdx.x] : 0;
+        rs_sync();
+        return r;
+    }
+#ifdef RS_TIMING
+    const long long tq1 = clock64();
+#endif
+    // ---- epilogue: thread = correspondence ----
+    const int grp = warp >> 3, hf = (warp >> 2) & 1, qd = warp & 3;
+    const int ntiles = (K + RT_TILE - 1) / RT_TILE;
+    // issue-path constants of this warp's group
+    const uint32_t tmem_grp = sm.tmem_base + (uint32_t)(grp * 256);
+    const uint32_t a_lo0 = rt_desc_lo(sm.u.tc.a_ring[0]), b1_lo = rt_desc_lo(sm.u.tc.b_op[grp][0]), b2_lo = rt_desc_lo(sm.u.tc.b_op[grp][1]);
+    const uint32_t bar_acc = smem_u32(&sm.acc_full[grp][0]), bar_ae = smem_u32(&sm.a_empty[0]);
+    auto issue = [&](uint32_t g) {                                    // MMAs of A tile g into buffer g & 1 of this group (its stage is known to be full)
+        const uint32_t st = g & (RT_STAGES - 1);
+        rt_issue_tile(tmem_grp + (g & 1u) * 128u, a_lo0 + st * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_acc + (g & 1u) * 8u, bar_ae + st * 8u);
+    };
+    const bool feeder = (warp & 7) == 0;                              // warps 0 and 8: wait for the A tiles on behalf of their group
+    if (threadIdx.x == 0)
+        for (int i = 0; i < RT_STAGES - 1 && i < ntiles; ++i) rt_load_tile(sm, scratch, tile0 + (uint32_t)i, i);
+    if (feeder && lane == 0) {                                        // first two tiles of each group: both accumulator buffers
+        mbar_wait(&sm.a_full[tile0 & (RT_STAGES - 1)], (tile0 / RT_STAGES) & 1u);
+        issue(tile0);
+        if (ntiles > 1) { mbar_wait(&sm.a_full[(tile0 + 1u) & (RT_STAGES - 1)], ((tile0 + 1u) / RT_STAGES) & 1u); issue(tile0 + 1u); }
+    }
+    const uint32_t taddr = sm.tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 256 + hf * 64);
+    const f32x2 negT = pack2(-d2max, -d2max);
+    const int hl0 = grp * RT_HT + hf * 20;                            // flush-local index of this thread's first hypothesis
+    // one 32-column chunk: 5 hypothesis pairs; sign bit of d2~ - d2max -> count, |.| -> band test
+    auto process = [&](const float (&v)[32], int (&c10)[10], int i, int ch) {
+        float m = 3.0e38f;
+#pragma unroll
+        for (int pr = 0; pr < 5; ++pr) {
+            const f32x2 x = pack2(v[6 * pr], v[6 * pr + 1]), y = pack2(v[6 * pr + 2], v[6 * pr + 3]), z = pack2(v[6 * pr + 4], v[6 * pr + 5]);
+            const f32x2 d = fma2(x, x, fma2(y, y, fma2(z, z, negT)));                // d2~ - d2max of two hypotheses
+            float wa, wb;
+            unpack2(d, wa, wb);
+            c10[2 * pr] += (int)(__float_as_uint(wa) >> 31);
+            c10[2 * pr + 1] += (int)(__float_as_uint(wb) >> 31);
+            m = min3abs(m, wa, wb);
+        }
+        if (m <= band) {                                             // rare: some (h, c) of this chunk is too close to call -> the oracle's chain decides
+            const int c = i * RT_TILE + qd * 32 + lane;
+            if (c < K) {
+                float w[10];
+#pragma unroll
+                for (int pr = 0; pr < 5; ++pr) {
+                    const f32x2 x = pack2(v[6 * pr], v[6 * pr + 1]), y = pack2(v[6 * pr + 2], v[6 * pr + 3]), z = pack2(v[6 * pr + 4], v[6 * pr + 5]);
+                    unpack2(fma2(x, x, fma2(y, y, fma2(z, z, negT))), w[2 * pr], w[2 * pr + 1]);
+                }
+                const uint32_t fix = tc_recheck(sm, (uint32_t)c, base + hl0 + ch * 10, n - (hl0 + ch * 10), d2max, band, w);
+#pragma unroll
+                for (int k = 0; k < 10; ++k) c10[k] += (int)((fix >> k) & 1u) - (int)((fix >> (16 + k)) & 1u);
+            }
+        }
+    };
+    int c0[10], c1[10];                                               // inlier counts of this thread's 2 x 10 hypotheses over its correspondences
+#pragma unroll
+    for (int j = 0; j < 10; ++j) { c0[j] = 0; c1[j] = 0; }
+    float va[32], vb[32];
+    for (int i = 0; i < ntiles; ++i) {
+        const uint32_t gi = tile0 + (uint32_t)i; const int buf = (int)(gi & 1u);
+#ifdef RS_TIMING
+        const long long tw0 = clock64();
+#endif
+        RTR(0, i);
+        mbar_wait(&sm.acc_full[grp][buf], (gi >> 1) & 1u);
+        RTR(1, i);
+#ifdef RS_TIMING
+        const long long tw1 = clock64(); tq_wait += tw1 - tw0;
+#endif
+        tc_fence_after();
+        __syncwarp();
+        tmem_ld32_issue(taddr + (uint32_t)(buf * 128), va); tmem_ld32_issue(taddr + (uint32_t)(buf * 128 + 32), vb);
+        tmem_ld_wait(va); tmem_ld_pin(vb);
+        RTR(2, i);
+#ifdef RS_TIMING
+        const long long tx0 = clock64(); tq_x[0] += tx0 - tw1;
+#endif
+        if (feeder && i + 2 < ntiles)                                // A tile i + 2 has landed (copied five tiles ago): whoever issues its MMAs
+            mbar_wait(&sm.a_full[(gi + 2u) & (RT_STAGES - 1)], ((gi + 2u) / RT_STAGES) & 1u);      // after this warp's arrival may rely on it
+        tc_fence_before();
+        __syncwarp();
+        RTR(3, i);
+#ifdef RS_TIMING
+        tq_x[2] += clock64() - tx0;
+#endif
+        if (lane == 0 && atom_inc_acq_rel(&sm.acc_arrivals[grp][buf]) == 7u) {   // the last of the group's 8 warps feeds the tensor core
+            sm.acc_arrivals[grp][buf] = 0u;                          // nobody touches it again before acc_full of the buffer's next tile
+            if (i + 2 < ntiles) issue(gi + 2u);
+            RTR(7, i);
+        }
+        RTR(4, i);
+#ifdef RS_TIMING
+        tq_x[1] += clock64() - tx0;
+        const long long tw2 = clock64(); tq_ld += tw2 - tw1;
+#endif
+        process(va, c0, i, 0);
+        process(vb, c1, i, 1);
+        RTR(5, i);
+        if (threadIdx.x == 0 && i + RT_STAGES - 1 < ntiles)          // off the critical path: A tile i + 7 into the stage of tile i - 1
+            rt_load_tile(sm, scratch, gi + (uint32_t)(RT_STAGES - 1), i + RT_STAGES - 1);
+        RTR(6, i);
+#ifdef RS_TIMING
+        tq_math += clock64() - tw2;
+#endif
+    }
+#ifdef RS_TIMING
+    const long long tq2 = clock64();
+#endif
+    // ---- totals over the 128 lanes x tiles ----
+#pragma unroll
+    for (int j = 0; j < 20; ++j) {
+        const int tot = __reduce_add_sync(0xffffffffu, j < 10 ? c0[j % 10] : c1[j % 10]);
+        if (lane == j) atomicAdd(&sm.u.tc.cnt[hl0 + j], tot);
+    }
+    rs_sync();
+#ifdef RS_TRACE
+    if (trace_on) for (int k = threadIdx.x; k < 16 * RTR_EV * RTR_TILES; k += RS_THREADS) g_trace[k] = (&sm.trace[0][0])[k];
+    else if (blockIdx.x == 0 && tile0 < 40u) for (int k = threadIdx.x; k < 16 * RTR_EV * RTR_TILES; k += RS_THREADS) (&sm.trace[0][0])[k] = 0u;
+#endif
+    const int r = (int)threadIdx.x < n ? sm.u.tc.cnt[threadIdx.x] : 0;
+    if (threadIdx.x == 0) { sm.stat[2] = 0u; sm.stat[3] = 0u; }
+    rs_sync();
+#ifdef RS_TIMING
+    if (threadIdx.x == 0) {
+        atomicAdd(&g_rt_dbg[7], (unsigned long long)tq_x[2]);
+        atomicAdd(&g_rt_dbg[0], (unsigned long long)(tq1 - tq0)); atomicAdd(&g_rt_dbg[1], (unsigned long long)tq_wait); atomicAdd(&g_rt_dbg[2], (unsigned long long)tq_ld);
+        atomicAdd(&g_rt_dbg[3], (unsigned long long)tq_math); atomicAdd(&g_rt_dbg[4], (unsigned long long)(clock64() - tq2)); atomicAdd(&g_rt_dbg[5], 1ull);
+        atomicAdd(&g_rt_dbg[6], (unsigned long long)ntiles); atomicAdd(&g_rt_dbg2[3], (unsigned long long)tq_x[0]); atomicAdd(&g_rt_dbg2[4], (unsigned long long)tq_x[1]);
+    }
+#endif
+    return r | (1 << 30);
+}
+
 // stage 2 on n queue-1 entries starting at `base` (thread i takes entry base + i): Kabsch + distance check on dense warps, survivors -> queue 2
-template <bool RES>
-BFR_DEVINL void fit_block(RsSmem& sm, const float4* __restrict__ corr_p, int base, int n, float d2max)
+template <bool RES, bool TC>
+BFR_DEVINL void fit_block(RsSmem& sm, const float4* __restrict__ corr_p, uint32_t K, uint64_t seed, uint32_t pair_id, int base, int n, float d2max)
 {
     const int lane = threadIdx.x & 31;
     float R[9], t[3];
     bool ok = false; uint32_t h = 0;
     if ((int)threadIdx.x < n) {
-        const uint4 e = sm.q1[base + threadIdx.x];
-        h = e.x;
-        const uint32_t id[3] = { e.y, e.z, e.w };
+        h = sm.q1[base + threadIdx.x];
+        uint32_t id[3];
+        sample3(seed, pair_id, h, K, id);                             // regenerated: queue 1 only keeps the hypothesis index
         float s[3][3], q[3][3];
         if (RES) load_sample_smem(sm, id, s, q); else load_sample(corr_p, id, s, q);
         ok = hypothesis_fit(s, q, d2max, R, t);
@@ -205,59 +595,59 @@ BFR_DEVINL void fit_block(RsSmem& sm, const float4* __restrict__ corr_p, int bas
         pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
         if (ok) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) sm.q[k][pos] = R[k];
+            for (int k = 0; k < 9; ++k) q2<TC>(sm, k, pos) = R[k];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) sm.q[9 + k][pos] = t[k];
-            sm.qh[pos] = h;
+            for (int k = 0; k < 3; ++k) q2<TC>(sm, 9 + k, pos) = t[k];
+            q2h<TC>(sm, pos) = h;
         }
     }
 }
 
-BFR_DEVINL unsigned long long pack_count(int count, uint32_t h) { return ((unsigned long long)(uint32_t)count << 32) | (unsigned long long)(0xFFFFFFFFu - h); }
+struct RsTc { unsigned char* scratch; float s1max, qmax; uint32_t tile0; };
 
 // one work item: hypotheses [hb, he) of pair p.  CONF: Open3D confidence rule (hb = the pair's first hypothesis, one item per pair).
-template <bool RES, bool CONF>
+// TC: queue 2 is scored by the tensor-core filter (resident pairs only).
+template <bool RES, bool CONF, bool TC>
 BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K, uint64_t seed, uint32_t pair_id, uint32_t hb, uint32_t he,
-                            float d2max, float sim2, float confidence, unsigned long long& best, int& n_scored, long long (&tm)[3])
+                            float d2max, float sim2, float confidence, RsTc& tc, unsigned long long& best, int& n_scored, long long (&tm)[3])
 {
+    static_assert(!TC || (RES && !CONF), "the tensor-core filter serves resident pairs without the confidence rule");
     const int lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) { sm.qcount = 0; sm.q1count = 0; sm.seq_best = 0ull; sm.seq_bound = he - hb; sm.seq_stop = 0; }
-    if (RES) load_chunk<3, RS_CHUNK, RS_THREADS>(sm.chunk, corr_p, K, 0);
-    __syncthreads();
+    constexpr int FLUSH = TC ? RT_FLUSH : RS_THREADS;                 // hypotheses scored per pass over the correspondences
 
     if (!CONF) {
-        // fit one block of queue 1, then score a full block of queue 2 if there is one
-        auto fit_and_score = [&](int base, int n) {
-            RST(tm[1], fit_block<RES>(sm, corr_p, base, n, d2max));
-            __syncthreads();
-            const int qn = sm.qcount;
-            __syncthreads();
-            if (qn >= RS_THREADS) {
-                uint32_t h; int count, hi;
-                bool mine;
-                RST(tm[2], mine = score_queue<RES>(sm, corr_p, K, RS_THREADS, d2max, h, count, hi));
-                if (mine) { const unsigned long long pk = pack_count(count, h); best = pk > best ? pk : best; }
-                n_scored += RS_THREADS;
-                const int rem = qn - RS_THREADS;                           // move the overflow [RS_THREADS, qn) down to the front
-                float mv[12]; uint32_t mh = 0;
-                if ((int)threadIdx.x < rem) {
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) mv[k] = sm.q[k][RS_THREADS + threadIdx.x];
-                    mh = sm.qh[RS_THREADS + threadIdx.x];
+        // score blocks of FLUSH hypotheses off the top of queue 2 while it holds that many (`all`: whatever is left)
+        auto drain = [&](bool all) {
+            for (;;) {
+                const int qn = sm.qcount;
+                rs_sync();                                            // everyone has read qcount
+                const int n = qn >= FLUSH ? FLUSH : (all ? qn : 0);
+                if (n == 0) break;
+                const int base = qn - n;
+                if (TC) {
+                    int count;
+                    RST(tm[2], count = tc_flush(sm, K, base, n, d2max, tc.s1max, tc.qmax, tc.scratch, tc.tile0));
+                    if (count & (1 << 30)) { tc.tile0 += (uint32_t)((K + RT_TILE - 1) / RT_TILE); count &= ~(1 << 30); }
+                    if ((int)threadIdx.x < n) { const unsigned long long pk = pack_count(count, sm.u.tc.qh[base + threadIdx.x]); best = pk > best ? pk : best; }
+                } else {
+                    uint32_t h; int count, hi;
+                    bool mine;
+                    RST(tm[2], mine = (score_queue<RES, false>(sm, corr_p, K, base, n, d2max, reinterpret_cast<int*>(sm.q1), h, count, hi)));
+                    if (mine) { const unsigned long long pk = pack_count(count, h); best = pk > best ? pk : best; }
                 }
-                __syncthreads();
-                if ((int)threadIdx.x < rem) {
-#pragma unroll
-                    for (int k = 0; k < 12; ++k) sm.q[k][threadIdx.x] = mv[k];
-                    sm.qh[threadIdx.x] = mh;
-                }
-                if (threadIdx.x == 0) sm.qcount = rem;
-                __syncthreads();
+                n_scored += n;
+                if (threadIdx.x == 0) sm.qcount = base;
+                rs_sync();
             }
+        };
+        auto fit_and_score = [&](int base, int n) {
+            RST(tm[1], (fit_block<RES, TC>(sm, corr_p, (uint32_t)K, seed, pair_id, base, n, d2max)));
+            rs_sync();
+            drain(false);
         };
         for (uint32_t base = hb; base < he; base += RS_S1 * RS_THREADS) {
             // stage 1: RS_S1 independent hypotheses per thread (their sample gathers overlap), cheap checks only (~10 % survive at 70 % outliers)
-            uint32_t hh[RS_S1], id[RS_S1][3];
+            uint32_t hh[RS_S1];
             bool ok[RS_S1];
 #ifdef RS_TIMING
             const long long ts_ = clock64();
@@ -265,8 +655,7 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
 #pragma unroll
             for (int u = 0; u < RS_S1; ++u) {
                 hh[u] = base + (uint32_t)u * RS_THREADS + threadIdx.x;
-                id[u][0] = id[u][1] = id[u][2] = 0u;
-                ok[u] = hh[u] < he && precheck<RES>(sm, corr_p, (uint32_t)K, seed, pair_id, hh[u], sim2, id[u]);
+                ok[u] = hh[u] < he && precheck<RES>(sm, corr_p, (uint32_t)K, seed, pair_id, hh[u], sim2);
             }
 #ifdef RS_TIMING
             tm[0] += clock64() - ts_;
@@ -278,39 +667,32 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
                     int pos = 0;
                     if (lane == 0) pos = atomicAdd(&sm.q1count, __popc(bal));
                     pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-                    if (ok[u]) sm.q1[pos] = make_uint4(hh[u], id[u][0], id[u][1], id[u][2]);
+                    if (ok[u]) sm.q1[pos] = hh[u];
                 }
             }
-            __syncthreads();
+            rs_sync();
             const int n1 = sm.q1count;
-            __syncthreads();                       // everyone has read q1count before it changes
+            rs_sync();                             // everyone has read q1count before it changes
             if (n1 >= RS_THREADS) {
                 int done = 0;
                 for (; n1 - done >= RS_THREADS; done += RS_THREADS) fit_and_score(done, RS_THREADS);
                 const int rem = n1 - done;                                 // < RS_THREADS leftovers move to the front
-                uint4 mv = make_uint4(0u, 0u, 0u, 0u);
+                uint32_t mv = 0u;
                 if ((int)threadIdx.x < rem) mv = sm.q1[done + threadIdx.x];
-                __syncthreads();
+                rs_sync();
                 if ((int)threadIdx.x < rem) sm.q1[threadIdx.x] = mv;
                 if (threadIdx.x == 0) sm.q1count = rem;
-                __syncthreads();
+                rs_sync();
             }
         }
         {
             const int n1 = sm.q1count;             // flush queue 1, then queue 2
-            __syncthreads();
+            rs_sync();
             if (n1 > 0) fit_and_score(0, n1);
             if (threadIdx.x == 0) sm.q1count = 0;
-            __syncthreads();
+            rs_sync();
         }
-        const int qn = sm.qcount;
-        if (qn > 0) {
-            uint32_t h; int count, hi;
-            bool mine;
-            RST(tm[2], mine = score_queue<RES>(sm, corr_p, K, qn, d2max, h, count, hi));
-            if (mine) { const unsigned long long pk = pack_count(count, h); best = pk > best ? pk : best; }
-            n_scored += qn;
-        }
+        drain(true);
     } else {
         // Open3D's convergence criterion, replayed exactly: rounds of RS_THREADS hypotheses in index order; every valid hypothesis of a round
         // is scored, then the round's (iteration, count) list is sorted by iteration and walked sequentially: a hypothesis only counts if its
@@ -324,37 +706,37 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
         for (uint32_t base = hb; base < he; base += RS_THREADS) {
             {
                 const uint32_t hh = base + threadIdx.x;
-                uint32_t id[3] = { 0u, 0u, 0u };
-                const bool ok = hh < he && precheck<RES>(sm, corr_p, (uint32_t)K, seed, pair_id, hh, sim2, id);
+                const bool ok = hh < he && precheck<RES>(sm, corr_p, (uint32_t)K, seed, pair_id, hh, sim2);
                 const unsigned bal = __ballot_sync(0xffffffffu, ok);
+                uint32_t* q1tail = reinterpret_cast<uint32_t*>(sm.q1) + 4 * RS_THREADS;    // srt_c's slice is free at this point
                 if (bal) {
                     int pos = 0;
                     if (lane == 0) pos = atomicAdd(&sm.q1count, __popc(bal));
                     pos = __shfl_sync(0xffffffffu, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-                    if (ok) sm.q1[pos] = make_uint4(hh, id[0], id[1], id[2]);
+                    if (ok) q1tail[pos] = hh;
                 }
             }
-            __syncthreads();
+            rs_sync();
             const int n1 = sm.q1count;
-            __syncthreads();
-            if (n1 > 0) fit_block<RES>(sm, corr_p, 0, n1, d2max);
-            __syncthreads();
+            rs_sync();
+            if (n1 > 0) fit_block<RES, false>(sm, corr_p, (uint32_t)K, seed, pair_id, 4 * RS_THREADS, n1, d2max);
+            rs_sync();
             const int qn = sm.qcount;
-            __syncthreads();
+            rs_sync();
             if (threadIdx.x == 0) { sm.q1count = 0; sm.qcount = 0; }
             if (qn > 0) {
                 uint32_t h; int count, hi;
-                const bool mine = score_queue<RES>(sm, corr_p, K, qn, d2max, h, count, hi);
+                const bool mine = score_queue<RES, false>(sm, corr_p, K, 0, qn, d2max, reinterpret_cast<int*>(sm.q1), h, count, hi);
                 n_scored += qn;
                 if (mine) { res_h[hi] = h - hb; res_c[hi] = count; }          // iteration number relative to the pair's first hypothesis
-                __syncthreads();
+                rs_sync();
                 if ((int)threadIdx.x < qn) {                                   // rank by iteration number (all distinct)
                     const uint32_t my = res_h[threadIdx.x];
                     int rank = 0;
                     for (int k = 0; k < qn; ++k) rank += (res_h[k] < my) ? 1 : 0;
                     srt_h[rank] = my; srt_c[rank] = res_c[threadIdx.x];
                 }
-                __syncthreads();
+                rs_sync();
                 if (threadIdx.x == 0) {
                     unsigned long long sb = sm.seq_best; uint32_t bound = sm.seq_bound;
                     for (int k = 0; k < qn; ++k) {
@@ -370,10 +752,10 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
                     sm.seq_best = sb; sm.seq_bound = bound;
                 }
             }
-            __syncthreads();
+            rs_sync();
             if (sm.seq_stop || (base - hb) + RS_THREADS >= sm.seq_bound) break;   // block-uniform
         }
-        __syncthreads();
+        rs_sync();
         if (threadIdx.x == 0) best = sm.seq_best;
     }
 }
@@ -381,14 +763,33 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
 __global__ void __launch_bounds__(RS_THREADS, 1)
 ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_off, const int32_t* __restrict__ corr_cnt, int P, int splits,
               uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, float confidence,
-              unsigned long long* __restrict__ best_packed, int32_t* __restrict__ valid_count)
+              unsigned long long* __restrict__ best_packed, int32_t* __restrict__ valid_count, unsigned char* __restrict__ tc_scratch)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    RsSmem& sm = *reinterpret_cast<RsSmem*>(smem_raw);
+    extern __shared__ unsigned char smem_raw[];
+    RsSmem& sm = *reinterpret_cast<RsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const float d2max = __fmul_rn(dist_th, dist_th), sim2 = __fmul_rn(similar_th, similar_th);
     const bool conf = confidence > 0.0f && confidence < 1.0f;
+    const bool tc_on = tc_scratch != nullptr && !conf;                // kernel-uniform: tensor memory and the operand ring are set up
     const uint32_t nh = h_end - h_begin;
-    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (tc_on) {
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 2); }    // a stage is free once both accumulators' MMAs have read it
+            for (int t = 0; t < 4; ++t) { mbar_init(&sm.acc_full[t >> 1][t & 1], 1); sm.acc_arrivals[t >> 1][t & 1] = 0u; }
+            mbar_fence_init();
+        }
+        if (warp == 0) tmem_alloc512(&sm.tmem_base);
+        for (int i = threadIdx.x; i < (int)sizeof(sm.u.tc.b_op) / 16; i += RS_THREADS) reinterpret_cast<uint4*>(sm.u.tc.b_op)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (threadIdx.x < 4) sm.stat[threadIdx.x] = 0u;
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+
+    RsTc tc;
+    tc.scratch = tc_on ? tc_scratch + (size_t)blockIdx.x * RT_MAX_TILES * RT_TILE_BYTES : nullptr;
+    tc.s1max = 0.0f; tc.qmax = 0.0f; tc.tile0 = 0u;
     long long tm[3] = { 0, 0, 0 };                                    // RS_TIMING: stage 1 / fit / score cycles (dead code otherwise)
 #ifdef RS_TIMING
     const long long t_begin = clock64();
@@ -404,13 +805,19 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         const uint32_t pair_id = pair_id_base + (uint32_t)p;
         unsigned long long best = 0ull;
         int n_scored = 0;                                             // hypotheses that passed every check (thread 0's tally)
-        __syncthreads();                                              // the previous item is done with shared memory
+        rs_sync();                                                    // the previous item is done with shared memory
+        if (threadIdx.x == 0) { sm.qcount = 0; sm.q1count = 0; sm.seq_best = 0ull; sm.seq_bound = he - hb; sm.seq_stop = 0; }
         if (K <= RS_CHUNK) {
-            if (conf) ransac_item<true, true>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, best, n_scored, tm);
-            else      ransac_item<true, false>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, best, n_scored, tm);
+            load_chunk<3, RS_CHUNK, RS_THREADS>(sm.chunk, corr_p, K, 0);
+            rs_sync();
+            if (conf) ransac_item<true, true, false>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, tc, best, n_scored, tm);
+            else if (tc_on && tc_prepare_pair(sm, K, tc.scratch, tc.s1max, tc.qmax))
+                ransac_item<true, false, true>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, tc, best, n_scored, tm);
+            else ransac_item<true, false, false>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, tc, best, n_scored, tm);
         } else {
-            if (conf) ransac_item<false, true>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, best, n_scored, tm);
-            else      ransac_item<false, false>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, best, n_scored, tm);
+            rs_sync();
+            if (conf) ransac_item<false, true, false>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, tc, best, n_scored, tm);
+            else      ransac_item<false, false, false>(sm, corr_p, K, seed, pair_id, hb, he, d2max, sim2, confidence, tc, best, n_scored, tm);
         }
         if (valid_count && threadIdx.x == 0 && n_scored) atomicAdd(valid_count + p, n_scored);
 #ifdef RS_TIMING
@@ -419,14 +826,19 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         // block max -> one atomic
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o); best = other > best ? other : best; }
-        __syncthreads();
-        if (lane == 0) sm.red[threadIdx.x >> 5] = best;
-        __syncthreads();
+        rs_sync();
+        if (lane == 0) sm.red[warp] = best;
+        rs_sync();
         if (threadIdx.x == 0) {
             unsigned long long b = 0ull;
             for (int w = 0; w < RS_WARPS; ++w) b = sm.red[w] > b ? sm.red[w] : b;
             if (b) atomicMax(best_packed + p, b);
         }
+    }
+    if (tc_on) {
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 0) tmem_dealloc512(sm.tmem_base);
     }
 #ifdef RS_TIMING
     if (threadIdx.x == 0) {
@@ -692,9 +1104,15 @@ lrf_vote_select_kernel(const float4* __restrict__ corr, const int32_t* __restric
     if (threadIdx.x == 0) { sub_cnt[p] = base_s; if (best_idx) best_idx[p] = (int64_t)hbest; }
 }
 
+#ifdef RS_TRACE
+}
+extern "C" __attribute__((visibility("default"))) unsigned bfr_dbg_ransac_trace(unsigned* out) { cudaMemcpyFromSymbol(out, bfr::g_trace, sizeof(unsigned) * 16 * 8 * 20); return 16 * 8 * 20; }
+namespace bfr {
+#endif
 #ifdef RS_TIMING
 }
 extern "C" __attribute__((visibility("default"))) void bfr_dbg_ransac_counters(unsigned long long* out) { cudaMemcpyFromSymbol(out, bfr::g_rs_dbg, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(bfr::g_rs_dbg, z, 64); }
+extern "C" __attribute__((visibility("default"))) void bfr_dbg_ransac_tc_counters(unsigned long long* out) { cudaMemcpyFromSymbol(out, bfr::g_rt_dbg, 64); cudaMemcpyFromSymbol(out + 8, bfr::g_rt_dbg2, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(bfr::g_rt_dbg, z, 64); cudaMemcpyToSymbol(bfr::g_rt_dbg2, z, 64); }
 namespace bfr {
 #endif
 // ---- host launchers -------------------------------------------------------------------------------------------
@@ -711,21 +1129,35 @@ static int sm_count()
     return v;
 }
 
+size_t ransac_scratch_bytes() { return (size_t)RS_MAX_CTAS * RT_MAX_TILES * RT_TILE_BYTES; }
+
+// -1 = not set (default: tensor-core scoring whenever scratch is available); 0 = exact FP32 scoring only; per thread like the K1 algorithm switch
+static thread_local int g_ransac_tc = -1;
+void ransac_set_tc(int on) { g_ransac_tc = on; }
+int ransac_get_tc() { return g_ransac_tc != 0 ? 1 : 0; }
+
+// tc_scratch: ransac_scratch_bytes() of device memory owned by this call (16-byte aligned), or nullptr / too small: every hypothesis is
+// scored by the exact FP32 loop.  The results are identical either way.
 cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int32_t* corr_cnt, int P, uint64_t seed, uint32_t pair_id_base,
                           uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, float confidence, int splits,
-                          unsigned long long* best_packed, int32_t* valid_count, cudaStream_t stream)
+                          unsigned long long* best_packed, int32_t* valid_count, void* tc_scratch, size_t tc_scratch_bytes, cudaStream_t stream)
 {
     static std::atomic<unsigned long long> attr_done{0};
-    cudaError_t e = ensure_dyn_smem((const void*)ransac_kernel, (int)sizeof(RsSmem), attr_done);
+    const size_t smem = sizeof(RsSmem) + 1024;
+    cudaError_t e = ensure_dyn_smem((const void*)ransac_kernel, (int)smem, attr_done);
     if (e != cudaSuccess) return e;
     if (P <= 0 || h_end <= h_begin) return cudaSuccess;
     const bool conf = confidence > 0.0f && confidence < 1.0f;
     if (splits < 1 || conf) splits = 1;                               // the convergence rule is sequential in the hypothesis index: one CTA per pair
     const long long items = (long long)P * splits;
-    const int sms = sm_count();
-    const unsigned grid = (unsigned)(items < sms ? items : sms);      // persistent: one 512-thread CTA per SM, items dealt round-robin
-    ransac_kernel<<<grid, RS_THREADS, sizeof(RsSmem), stream>>>(reinterpret_cast<const float4*>(corr), corr_off, corr_cnt, P, splits, seed, pair_id_base,
-                                                                h_begin, h_end, dist_th, similar_th, confidence, best_packed, valid_count);
+    int sms = sm_count();
+    if (sms > RS_MAX_CTAS) sms = RS_MAX_CTAS;
+    const unsigned grid = (unsigned)(items < sms ? items : sms);      // persistent: one CTA per SM, items dealt round-robin
+    unsigned char* scratch = reinterpret_cast<unsigned char*>(((uintptr_t)tc_scratch + 15) & ~(uintptr_t)15);
+    if (!tc_scratch || g_ransac_tc == 0 || (size_t)(scratch - reinterpret_cast<unsigned char*>(tc_scratch)) + (size_t)grid * RT_MAX_TILES * RT_TILE_BYTES > tc_scratch_bytes)
+        scratch = nullptr;
+    ransac_kernel<<<grid, RS_THREADS, smem, stream>>>(reinterpret_cast<const float4*>(corr), corr_off, corr_cnt, P, splits, seed, pair_id_base,
+                                                     h_begin, h_end, dist_th, similar_th, confidence, best_packed, valid_count, scratch);
     return cudaGetLastError();
 }
 

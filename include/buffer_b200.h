@@ -47,6 +47,10 @@ const char* bfr_error_string(int code);
  * implementation: 0 = FP32 FFMA2 kernel (every product in FP32), 1 = tensor-core (tcgen05, f16 operands) filter followed by an
  * exact FP32 re-check of the near-best candidates.  Both produce bit-identical outputs. */
 #define BFR_CFG_K1_ALGO 1
+/* BFR_CFG_RANSAC_TC selects how RANSAC scores its hypotheses on pairs of up to 5120 correspondences: 1 = tensor-core (tcgen05, 2-level f16
+ * operand splits) residual filter with an exact FP32 re-check of the (h, c) pairs too close to the threshold to call (needs the scratch
+ * workspace of bfr_ransac_workspace_bytes), 0 = every residual in FP32.  Both produce bit-identical outputs. */
+#define BFR_CFG_RANSAC_TC 2
 int bfr_config_set(int key, int value);
 int bfr_config_get(int key);
 
@@ -101,10 +105,15 @@ int bfr_gather_corr(const float* src_xyz, const float* tgt_xyz, const int64_t* s
  * every hypothesis of the range is evaluated.  In (0, 1) (ThreeDMatch/config.py:65 = 0.999): Open3D's rule, evaluated as by ONE
  * sequential thread - iteration i (= h - h_begin) only runs while i < min(h_end - h_begin, ceil(log(1 - confidence) /
  * log(1 - (best_count / K)^3))) of the best hypothesis before it; the result is the best of exactly those iterations.  The rule
- * is sequential in h, so one call must cover the pair's whole range (no split over calls / GPUs) and `splits` is ignored. */
+ * is sequential in h, so one call must cover the pair's whole range (no split over calls / GPUs) and `splits` is ignored.
+ * ws / ws_bytes: bfr_ransac_workspace_bytes() of device scratch owned by this call until it has completed (the f16 operand tiles
+ * of the tensor-core scoring filter, which stay in L2).  ws = NULL (or too small): every hypothesis is scored by the exact FP32 loop -
+ * slower, identical results. */
+size_t bfr_ransac_workspace_bytes(void);
 int bfr_ransac_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,
                        uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end,
-                       float dist_th, float similar_th, float confidence, int splits, uint64_t* best_packed, int32_t* valid_count, void* stream);
+                       float dist_th, float similar_th, float confidence, int splits, uint64_t* best_packed, int32_t* valid_count,
+                       void* ws, size_t ws_bytes, void* stream);
 /* Decode best_packed and regenerate the winning minimal-sample fit: T [P][16] row-major 4x4 (result.transformation,
  * models/BUFFER.py:326), inlier count and hypothesis index (-1 if none; T = identity). */
 int bfr_ransac_finalize_batched(const float* corr_xyz, const int32_t* corr_off, const int32_t* corr_cnt, int P,

@@ -68,13 +68,13 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.bfr_mutual_nn_workspace_bytes(2, 5000, 5000) >= 2 * 2 * 5120 * 12
     assert L.bfr_register_workspace_bytes(2, 100, 100, 200, 200) > 0 and L.bfr_score_workspace_bytes(10) >= 320
     assert L.bfr_mutual_matching_batched(None, None, None, None, 1, 1, 1, 1, 1, 32, 1, None, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
-    assert L.bfr_ransac_batched(None, None, None, 0, 0, 0, 0, 0, 0.1, 0.8, 1.0, 1, None, None, None) == 0     # P == 0 is a no-op
+    assert L.bfr_ransac_batched(None, None, None, 0, 0, 0, 0, 0, 0.1, 0.8, 1.0, 1, None, None, None, 0, None) == 0     # P == 0 is a no-op
     assert L.bfr_rigid_transform_3d(None, None, None, 3, 3, 0.0, None, None) == -1
     # more than BFR_MAX_PAIRS pairs in one call is an argument error (BFR_E_SIZE), reported before anything touches the device
     buf = ctypes.create_string_buffer(64)
     ptr = ctypes.cast(buf, ctypes.c_void_p)
     assert L.bfr_mutual_matching_batched(ptr, ptr, ptr, ptr, 70000, 1, 1, 1, 1, 32, 1, None, None, None, None, None, None, None, None, None, None, ptr, 1 << 40, None) == -2
-    assert L.bfr_ransac_batched(ptr, ptr, ptr, 70000, 0, 0, 0, 10, 0.1, 0.8, 1.0, 1, ptr, None, None) == -2
+    assert L.bfr_ransac_batched(ptr, ptr, ptr, 70000, 0, 0, 0, 10, 0.1, 0.8, 1.0, 1, ptr, None, None, 0, None) == -2
     # int32 row offsets: P * M beyond INT32_MAX is refused up front (no copy is queued), the size query reports 0
     assert L.bfr_register_host_workspace_bytes(60000, 40000, 40000, 32) == 0
     assert L.bfr_register_uniform_host(ptr, ptr, ptr, ptr, 60000, 40000, 40000, 32, 10, 0, 0, 0.1, 0.8, 1.0, 0.1, 20, 1, ptr, None, None, ptr, 1 << 40, None) == -2

@@ -8,6 +8,7 @@ if os.environ.get("BFR_SO"): _lib.SO_PATH = os.path.abspath(os.environ["BFR_SO"]
 from buffer_b200 import backend as B, synthetic as S
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 1623
 splits = [int(x) for x in sys.argv[2:]] or [1, 2, 3, 4]
+if os.environ.get("BFR_RANSAC_FP32"): B.set_ransac_scoring(0)
 c = S.CONFIGS[int(os.environ.get("BFR_CFG", "2"))]; N = c["gen"]["num_kpts"]; dev = "cuda:0"
 parts = [S.make_pairs(min(128, P - p0), first_pair=p0, device=dev, **c["gen"]) for p0 in range(0, P, 128)]
 cat = lambda f: torch.cat([getattr(b, f) for b in parts], 0)
@@ -33,3 +34,9 @@ for s in splits:
         o = np.zeros(8, dtype=np.uint64); L.bfr_dbg_ransac_counters(ctypes.c_void_p(o.ctypes.data))
         tot, sc, fit, n, nsc = [float(x) for x in o[:5]]
         print("  per CTA: total %.0f cycles = stage1 %.0f + fit %.0f + score %.0f; scored hypotheses/CTA %.1f" % (tot / n, (tot - fit) / n, (fit - sc) / n, sc / n, nsc / n))
+        if hasattr(L, "bfr_dbg_ransac_tc_counters"):
+            o = np.zeros(16, dtype=np.uint64); L.bfr_dbg_ransac_tc_counters(ctypes.c_void_p(o.ctypes.data))
+            b, w, ld, m, r, nf, nt = [float(x) for x in o[:7]]
+            if o[10]: print("  issue path per issue: a_empty wait + TMA %.0f, a_full wait + MMA issue %.0f (%d issues); thread 0 per tile: tcgen05.ld %.0f, hand-back %.0f" % (float(o[8]) / float(o[10]), float(o[9]) / float(o[10]), int(o[10]), float(o[11]) / nt, float(o[12]) / nt))
+            if o[10]: print("  per issue: a_full wait %.0f, fence + 2 MMAs %.0f, 2 commits %.0f; thread 0 per tile: fence + syncwarp %.0f" % (float(o[13]) / float(o[10]), float(o[14]) / float(o[10]), float(o[15]) / float(o[10]), float(o[7]) / nt))
+            if nf: print("  tensor flush (thread 0): %.0f flushes/CTA, %.1f tiles/flush; cycles per flush: build %.0f, acc wait %.0f, tmem ld %.0f, math %.0f, reduce %.0f" % (nf / n, nt / nf, b / nf, w / nf, ld / nf, m / nf, r / nf))

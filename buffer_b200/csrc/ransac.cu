@@ -33,8 +33,9 @@
 
 namespace bfr {
 
-constexpr int RS_THREADS = 512;                 // worker threads: stage 1, fits, scoring / tensor-core epilogue
+constexpr int RS_THREADS = 384;                 // worker threads: stage 1, fits, scoring / tensor-core epilogue
 constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_LAUNCH = RS_THREADS + 32;      // + the warp that feeds the tensor core (TMA of the A tiles, tcgen05.mma issue): 13 warps, <= 152 registers
 constexpr int RS_CHUNK = 5120;                  // correspondences per shared-memory chunk; pairs with K <= RS_CHUNK stay resident
 #ifndef RS_S1_N
 #define RS_S1_N 4
@@ -45,8 +46,10 @@ constexpr int RS_Q1CAP = (1 + RS_S1) * RS_THREADS; // queue 1 holds < RS_THREADS
 constexpr int RS_MAX_CTAS = 160;                   // upper bound of the persistent grid (sizes the tensor-core scratch)
 
 // tensor-core scoring filter
-constexpr int RT_HT = 40;                       // hypotheses per accumulator tile: 4 chunks of 32 TMEM columns = 5 hypothesis pairs x (x x' y y' z z') + 2 unused
-constexpr int RT_FLUSH = 2 * RT_HT;             // hypotheses per flush: two warp groups, each ping-ponging between two 128 x 128 accumulator tiles (512 TMEM columns)
+constexpr int RT_GROUPS = RS_WARPS / 4;         // warp groups of the epilogue: 4 warps = the 128 TMEM lanes (correspondences) of a tile
+constexpr int RT_HT = 20;                       // hypotheses per accumulator tile: 2 chunks of 32 TMEM columns = 5 hypothesis pairs x (x x' y y' z z') + 2 unused
+constexpr int RT_FLUSH = RT_GROUPS * RT_HT;     // hypotheses per flush = one 128 x 192 accumulator tile (a group reads its 64-column slice); two tiles ping-pong
+constexpr int RT_N = RT_GROUPS * 64;            // MMA N: small MMAs cost ~80 cycles each whatever their N (tools/microbench/mma_issue.cu), so one pair serves all groups
 constexpr int RT_QCAP = RT_FLUSH + RS_THREADS;  // queue 2 (tensor-core scoring): < RT_FLUSH leftovers plus the survivors of one fit block
 constexpr int RT_TILE = 128;                    // correspondences per A tile (MMA M)
 constexpr int RT_TILE_BYTES = RT_TILE * 32;     // K = 16 f16 per row
@@ -80,7 +83,7 @@ struct __align__(1024) RsSmem {
         } ex;
         struct {                                // tensor-core scoring
             unsigned char a_ring[RT_STAGES][RT_TILE_BYTES];   // A tiles: 128 correspondences x 16 f16, unswizzled K-major core matrices
-            unsigned char b_op[2][2][128 * 32];               // [warp group][B1 | B2]: 128 (hypothesis, component) rows x 16 f16
+            unsigned char b_op[2][RT_N * 32];                 // [B1 | B2]: 192 (hypothesis, component) rows x 16 f16
             float q[12][RT_QCAP];
             uint32_t qh[RT_QCAP];
             int cnt[RT_FLUSH];                                // inlier counts of the hypotheses of the current flush
@@ -88,8 +91,8 @@ struct __align__(1024) RsSmem {
     } u;
     uint32_t q1[RS_Q1CAP];                      // queue 1: survivors of the cheap checks (hypothesis index); idle: partial counts / round results
     unsigned long long red[RS_WARPS];
-    uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_full[2][2];     // acc_full[warp group][accumulator buffer]
-    uint32_t acc_arrivals[2][2];                // epilogue warps that have pulled the buffer's tile out of TMEM (the 8th issues the MMAs of the tile after next)
+    uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_full[2], acc_empty[2];     // acc_*[accumulator buffer]
+    int tc_ntiles;                              // A tiles of the current item; < 0: the tensor-core warp leaves
     unsigned long long seq_best;                // confidence mode: state of the sequential replay
     uint32_t seq_bound;
     int seq_stop;
@@ -114,7 +117,9 @@ struct __align__(16) ScSmem {
     unsigned long long red[SC_THREADS / 32];
 };
 
-BFR_DEVINL void rs_sync() { __syncthreads(); }
+// barrier of the worker threads (the tensor-core warp is not part of it) / of all threads (hands a flush to the tensor-core warp)
+BFR_DEVINL void rs_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RS_THREADS) : "memory"); }
+BFR_DEVINL void rs_sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(RS_LAUNCH) : "memory"); }
 
 // cooperative load of correspondences [c0, c0 + CHUNK) of one pair (8-float records) into the pair-interleaved layout
 template <int NF, int CHUNK, int THREADS>
@@ -302,29 +307,21 @@ BFR_DEVINL bool tc_prepare_pair(RsSmem& sm, int K, unsigned char* __restrict__ s
     fence_proxy_async_all();                    // the scratch is read by the async proxy (TMA)
     rs_sync();
     s1max = __uint_as_float(sm.stat[0]); qmax = __uint_as_float(sm.stat[1]);
+    if (threadIdx.x == 0) sm.tc_ntiles = ntiles;
     return sm.stat[3] == 0u;
 }
 
-// Feeding the tensor core (single threads of the epilogue warps; there is no dedicated warp: 17 warps would cut the register budget
-// to 96).  Tile numbers `g` run on across flushes and items, so every mbarrier just keeps flipping phases.
-//  * rt_load_tile: 1-D TMA copy of A tile i of the item into its ring stage, once both groups' MMAs on the stage's previous occupant
-//    have completed (a_empty: two tcgen05.commit arrivals per use).
-//  * rt_issue_tile: the two MMAs of an A tile into one accumulator buffer (B1 then B2 accumulate), commit -> acc_full and a_empty.  It
-//    sits on the critical path buffer handed back -> buffer full again, so everything is precomputed: the caller passes the low words of
-//    the three shared-memory descriptors (the high word is the same for all) and the two barrier addresses.
-BFR_DEVINL void rt_load_tile(RsSmem& sm, const unsigned char* __restrict__ scratch, uint32_t g, int i)
-{
-    const int s = (int)(g % RT_STAGES);
-    mbar_wait(&sm.a_empty[s], ((g / RT_STAGES) & 1u) ^ 1u);
-    mbar_expect_tx(&sm.a_full[s], RT_TILE_BYTES);
-    tma_load_1d(sm.u.tc.a_ring[s], scratch + (size_t)i * RT_TILE_BYTES, RT_TILE_BYTES, &sm.a_full[s]);
-}
+// Feeding the tensor core: one thread of the dedicated 13th warp.  Tile numbers `g` run on across flushes and items, so every mbarrier
+// just keeps flipping phases.  Per flush it polls, round-robin over the warp groups, for "this group's next accumulator buffer has been
+// handed back and the A tile has landed" and issues that tile's two MMAs (B1 then B2 accumulate; commit -> acc_full of the buffer and
+// a_empty of the A stage), and keeps the TMA ring of A tiles full.  Everything on that path is precomputed: low words of the
+// shared-memory descriptors (the high word is the same for all) and barrier addresses.
 constexpr uint32_t RT_DESC_HI = 16u | (1u << 14);                    // SBO = 256 B (8-row groups), descriptor version 1, no swizzle
 BFR_DEVINL uint32_t rt_desc_lo(const void* smem) { return ((smem_u32(smem) >> 4) & 0x3FFFu) | (8u << 16); }     // LBO = 128 B (K direction)
 BFR_DEVINL void rt_issue_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t b1_lo, uint32_t b2_lo, uint32_t bar_acc_full, uint32_t bar_a_empty)
 {
-    // instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 128, M = 128
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 192, M = 128
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(RT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     asm volatile("{\n\t.reg .b64 da, db1, db2;\n\t.reg .pred pt, pf;\n\t"
                  "mov.b64 da, {%1, %4};\n\tmov.b64 db1, {%2, %4};\n\tmov.b64 db2, {%3, %4};\n\t"
                  "setp.eq.u32 pt, %0, %0;\n\tsetp.ne.u32 pf, %0, %0;\n\t"
@@ -336,15 +333,44 @@ BFR_DEVINL void rt_issue_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t b1_lo, ui
                  ::"r"(tmem_d), "r"(a_lo), "r"(b1_lo), "r"(b2_lo), "r"(RT_DESC_HI), "r"(idesc), "r"(bar_acc_full), "r"(bar_a_empty) : "memory");
 }
 static_assert(RT_STAGES == 8, "the ring index is taken with a mask");
-BFR_DEVINL uint32_t atom_inc_acq_rel(uint32_t* p)
+BFR_DEVINL bool mbar_test(uint32_t bar, uint32_t parity)
 {
-    uint32_t old;
-#ifdef RT_ATOM_RELAXED
-    asm volatile("atom.relaxed.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
-#else
-    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(p)) : "memory");
-#endif
-    return old;
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scratch)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t tmem_base = sm.tmem_base;
+    const uint32_t a_lo0 = rt_desc_lo(sm.u.tc.a_ring[0]), b1_lo = rt_desc_lo(sm.u.tc.b_op[0]), b2_lo = rt_desc_lo(sm.u.tc.b_op[1]);
+    const uint32_t bar_af = smem_u32(&sm.a_full[0]), bar_ae = smem_u32(&sm.a_empty[0]), bar_cf = smem_u32(&sm.acc_full[0]);
+    const uint32_t ring = smem_u32(sm.u.tc.a_ring[0]);
+    uint32_t g0 = 0;                                                  // A tiles consumed before this flush
+    for (;;) {
+        rs_sync_all();
+        const int ntiles = *reinterpret_cast<volatile int*>(&sm.tc_ntiles);
+        if (ntiles < 0) break;
+        if (lane == 0) {
+            auto load = [&](int j) {                                  // A tile j -> its ring stage, once the MMAs on the previous occupant have completed
+                const uint32_t gj = g0 + (uint32_t)j, st = gj & (RT_STAGES - 1);
+                mbar_wait(&sm.a_empty[st], ((gj / RT_STAGES) & 1u) ^ 1u);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_af + st * 8u), "r"((uint32_t)RT_TILE_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(ring + st * RT_TILE_BYTES), "l"(scratch + (size_t)j * RT_TILE_BYTES), "r"((uint32_t)RT_TILE_BYTES), "r"(bar_af + st * 8u) : "memory");
+            };
+            for (int j = 0; j < RT_STAGES - 1 && j < ntiles; ++j) load(j);
+            for (int i = 0; i < ntiles; ++i) {
+                const uint32_t gi = g0 + (uint32_t)i, st = gi & (RT_STAGES - 1), buf = gi & 1u;
+                mbar_wait(&sm.acc_empty[buf], ((gi >> 1) & 1u) ^ 1u);                 // every epilogue warp has pulled the buffer's previous tile out of TMEM
+                mbar_wait(&sm.a_full[st], (gi / RT_STAGES) & 1u);
+                rt_issue_tile(tmem_base + buf * 256u, a_lo0 + st * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_cf + buf * 8u, bar_ae + st * 8u);
+                if (i + RT_STAGES - 1 < ntiles) load(i + RT_STAGES - 1);             // into the stage of tile i - 1
+            }
+        }
+        g0 += (uint32_t)ntiles;
+        __syncwarp();
+    }
 }
 
 // Out of line (rare): correspondence c against the (up to) 10 hypotheses of one chunk, queue entries qbase .. qbase + 9 (the first
@@ -373,13 +399,13 @@ __device__ __noinline__ uint32_t tc_recheck(const RsSmem& sm, uint32_t c, int qb
     return fix;
 }
 
-// Score the queued hypotheses [base, base + n), n <= RT_FLUSH, on the tensor cores.  Warps 0-7 (group 0) own flush-local hypotheses
-// 0-39, warps 8-15 (group 1) hypotheses 40-79.  A group's 40 hypotheses x 3 components are the 128 columns of an accumulator tile (4
-// chunks of 32 columns; a chunk holds 10 hypotheses as 5 pairs (x_a x_b y_a y_b z_a z_b) so that one FFMA2 squares a component of two
-// hypotheses) and the group ping-pongs between two such tiles: while its threads work on the tile of A tile i (thread = correspondence:
-// warp w reads TMEM lanes 32 (w % 4) .., column half (w / 4) % 2), the tensor core fills the other buffer with A tile i + 1.  A warp pulls
-// its 64 columns into registers, hands the buffer back, and only then does the arithmetic; the last of the 8 warps to hand it back
-// issues the MMAs of A tile i + 2.  `tile0` = A tiles consumed before this flush (the mbarrier phase clock).
+// Score the queued hypotheses [base, base + n), n <= RT_FLUSH, on the tensor cores.  The flush's 60 hypotheses x 3 components are the 192
+// columns of an accumulator tile; warp group g (warps 4g .. 4g + 3) reads columns 64 g .. 64 g + 63 = flush-local hypotheses 20g .. 20g + 19
+// (2 chunks of 32 columns; a chunk holds 10 hypotheses as 5 pairs (x_a x_b y_a y_b z_a z_b) so that one FFMA2 squares a component of two
+// hypotheses).  Two tiles ping-pong: while the threads work on the tile of A tile i (thread = correspondence: warp w reads TMEM lanes
+// 32 (w % 4) ..), the tensor core fills the other buffer with A tile i + 1.  A warp pulls its 64 columns into registers, hands the buffer
+// back to the tensor-core warp (which issues A tile i + 2 once all 12 warps have), and only then does the arithmetic.
+// `tile0` = A tiles consumed before this flush (the mbarrier phase clock).
 // Returns, in threads < n, the exact inlier count of hypothesis base + threadIdx.x; bit 30 is set (in every thread) if the tensor-core path
 // ran, i.e. ceil(K / 128) A tiles were consumed.  Out of line: ransac_item flushes from three places.
 __device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d2max, float s1max, float qmax, const unsigned char* __restrict__ scratch, uint32_t tile0)
@@ -404,9 +430,10 @@ __device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d
         const __half zero = __float2half_rn(0.0f), m1 = __float2half_rn(-1.0f);
         const __half e0 = comp == 0 ? m1 : zero, e1 = comp == 1 ? m1 : zero, e2 = comp == 2 ? m1 : zero;
         const int grp = hl / RT_HT, hh = hl - grp * RT_HT, ch = hh / 10, k = hh - ch * 10;
-        const int col = ch * 32 + (k >> 1) * 6 + comp * 2 + (k & 1);
-        unsigned char* b1 = sm.u.tc.b_op[grp][0] + rt_row_offset(col);
-        unsigned char* b2 = sm.u.tc.b_op[grp][1] + rt_row_offset(col);
+        static_assert(RT_HT == 20, "two chunks of ten hypotheses per group");
+        const int col = grp * 64 + ch * 32 + (k >> 1) * 6 + comp * 2 + (k & 1);
+        unsigned char* b1 = sm.u.tc.b_op[0] + rt_row_offset(col);
+        unsigned char* b2 = sm.u.tc.b_op[1] + rt_row_offset(col);
         *reinterpret_cast<uint4*>(b1) = make_uint4(pack_h2(h0, h1), pack_h2(h2, h0), pack_h2(h1, h2), pack_h2(ht, e0));
         *reinterpret_cast<uint4*>(b1 + 128) = make_uint4(pack_h2(e1, e2), pack_h2(e0, e1), pack_h2(e2, zero), 0u);
         *reinterpret_cast<uint4*>(b2) = make_uint4(pack_h2(l0, l1), pack_h2(l2, zero), 0u, pack_h2(lt, zero));
@@ -445,27 +472,12 @@ __device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d
     const long long tq1 = clock64();
 #endif
     // ---- epilogue: thread = correspondence ----
-    const int grp = warp >> 3, hf = (warp >> 2) & 1, qd = warp & 3;
+    rs_sync_all();                              // the tensor-core warp starts on this flush
+    const int grp = warp >> 2, qd = warp & 3;
     const int ntiles = (K + RT_TILE - 1) / RT_TILE;
-    // issue-path constants of this warp's group
-    const uint32_t tmem_grp = sm.tmem_base + (uint32_t)(grp * 256);
-    const uint32_t a_lo0 = rt_desc_lo(sm.u.tc.a_ring[0]), b1_lo = rt_desc_lo(sm.u.tc.b_op[grp][0]), b2_lo = rt_desc_lo(sm.u.tc.b_op[grp][1]);
-    const uint32_t bar_acc = smem_u32(&sm.acc_full[grp][0]), bar_ae = smem_u32(&sm.a_empty[0]);
-    auto issue = [&](uint32_t g) {                                    // MMAs of A tile g into buffer g & 1 of this group (its stage is known to be full)
-        const uint32_t st = g & (RT_STAGES - 1);
-        rt_issue_tile(tmem_grp + (g & 1u) * 128u, a_lo0 + st * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_acc + (g & 1u) * 8u, bar_ae + st * 8u);
-    };
-    const bool feeder = (warp & 7) == 0;                              // warps 0 and 8: wait for the A tiles on behalf of their group
-    if (threadIdx.x == 0)
-        for (int i = 0; i < RT_STAGES - 1 && i < ntiles; ++i) rt_load_tile(sm, scratch, tile0 + (uint32_t)i, i);
-    if (feeder && lane == 0) {                                        // first two tiles of each group: both accumulator buffers
-        mbar_wait(&sm.a_full[tile0 & (RT_STAGES - 1)], (tile0 / RT_STAGES) & 1u);
-        issue(tile0);
-        if (ntiles > 1) { mbar_wait(&sm.a_full[(tile0 + 1u) & (RT_STAGES - 1)], ((tile0 + 1u) / RT_STAGES) & 1u); issue(tile0 + 1u); }
-    }
-    const uint32_t taddr = sm.tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 256 + hf * 64);
+    const uint32_t taddr = sm.tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 64);
     const f32x2 negT = pack2(-d2max, -d2max);
-    const int hl0 = grp * RT_HT + hf * 20;                            // flush-local index of this thread's first hypothesis
+    const int hl0 = grp * RT_HT;                                      // flush-local index of this thread's first hypothesis
     // one 32-column chunk: 5 hypothesis pairs; sign bit of d2~ - d2max -> count, |.| -> band test
     auto process = [&](const float (&v)[32], int (&c10)[10], int i, int ch) {
         float m = 3.0e38f;
@@ -497,60 +509,38 @@ __device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d
     int c0[10], c1[10];                                               // inlier counts of this thread's 2 x 10 hypotheses over its correspondences
 #pragma unroll
     for (int j = 0; j < 10; ++j) { c0[j] = 0; c1[j] = 0; }
+#ifdef RT_STAGGER
+    // The 12 warps are released by the same barrier and would run their phases (wait, tcgen05.ld, hand-back: latency; arithmetic: issue
+    // slots) in lock step; a one-time offset between the groups lets one group's arithmetic cover another's latencies.  The two-tile
+    // depth of the accumulator pipeline keeps the offset alive.
+    if (grp) { const long long t_ = clock64(); while (clock64() - t_ < (long long)(grp * RT_STAGGER)) { } }
+#endif
     float va[32], vb[32];
     for (int i = 0; i < ntiles; ++i) {
-        const uint32_t gi = tile0 + (uint32_t)i; const int buf = (int)(gi & 1u);
-#ifdef RS_TIMING
-        const long long tw0 = clock64();
-#endif
+        const uint32_t gi = tile0 + (uint32_t)i; const uint32_t buf = gi & 1u;
         RTR(0, i);
-        mbar_wait(&sm.acc_full[grp][buf], (gi >> 1) & 1u);
+        mbar_wait(&sm.acc_full[buf], (gi >> 1) & 1u);
         RTR(1, i);
-#ifdef RS_TIMING
-        const long long tw1 = clock64(); tq_wait += tw1 - tw0;
-#endif
         tc_fence_after();
         __syncwarp();
-        tmem_ld32_issue(taddr + (uint32_t)(buf * 128), va); tmem_ld32_issue(taddr + (uint32_t)(buf * 128 + 32), vb);
+        tmem_ld32_issue(taddr + buf * 256u, va); tmem_ld32_issue(taddr + buf * 256u + 32u, vb);
         tmem_ld_wait(va); tmem_ld_pin(vb);
         RTR(2, i);
-#ifdef RS_TIMING
-        const long long tx0 = clock64(); tq_x[0] += tx0 - tw1;
-#endif
-        if (feeder && i + 2 < ntiles)                                // A tile i + 2 has landed (copied five tiles ago): whoever issues its MMAs
-            mbar_wait(&sm.a_full[(gi + 2u) & (RT_STAGES - 1)], ((gi + 2u) / RT_STAGES) & 1u);      // after this warp's arrival may rely on it
         tc_fence_before();
         __syncwarp();
         RTR(3, i);
-#ifdef RS_TIMING
-        tq_x[2] += clock64() - tx0;
-#endif
-        if (lane == 0 && atom_inc_acq_rel(&sm.acc_arrivals[grp][buf]) == 7u) {   // the last of the group's 8 warps feeds the tensor core
-            sm.acc_arrivals[grp][buf] = 0u;                          // nobody touches it again before acc_full of the buffer's next tile
-            if (i + 2 < ntiles) issue(gi + 2u);
-            RTR(7, i);
-        }
+        if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);              // the buffer goes back to the tensor-core warp
         RTR(4, i);
-#ifdef RS_TIMING
-        tq_x[1] += clock64() - tx0;
-        const long long tw2 = clock64(); tq_ld += tw2 - tw1;
-#endif
         process(va, c0, i, 0);
         process(vb, c1, i, 1);
         RTR(5, i);
-        if (threadIdx.x == 0 && i + RT_STAGES - 1 < ntiles)          // off the critical path: A tile i + 7 into the stage of tile i - 1
-            rt_load_tile(sm, scratch, gi + (uint32_t)(RT_STAGES - 1), i + RT_STAGES - 1);
-        RTR(6, i);
-#ifdef RS_TIMING
-        tq_math += clock64() - tw2;
-#endif
     }
 #ifdef RS_TIMING
     const long long tq2 = clock64();
 #endif
     // ---- totals over the 128 lanes x tiles ----
 #pragma unroll
-    for (int j = 0; j < 20; ++j) {
+    for (int j = 0; j < RT_HT; ++j) {
         const int tot = __reduce_add_sync(0xffffffffu, j < 10 ? c0[j % 10] : c1[j % 10]);
         if (lane == j) atomicAdd(&sm.u.tc.cnt[hl0 + j], tot);
     }
@@ -760,7 +750,7 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS, 1)
+__global__ void __launch_bounds__(RS_LAUNCH, 1)
 ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_off, const int32_t* __restrict__ corr_cnt, int P, int splits,
               uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, float confidence,
               unsigned long long* __restrict__ best_packed, int32_t* __restrict__ valid_count, unsigned char* __restrict__ tc_scratch)
@@ -769,22 +759,33 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
     RsSmem& sm = *reinterpret_cast<RsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const float d2max = __fmul_rn(dist_th, dist_th), sim2 = __fmul_rn(similar_th, similar_th);
     const bool conf = confidence > 0.0f && confidence < 1.0f;
-    const bool tc_on = tc_scratch != nullptr && !conf;                // kernel-uniform: tensor memory and the operand ring are set up
+    const bool tc_on = tc_scratch != nullptr && !conf;                // kernel-uniform: the tensor-core warp serves this launch
     const uint32_t nh = h_end - h_begin;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (tc_on) {
         if (threadIdx.x == 0) {
-            for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 2); }    // a stage is free once both accumulators' MMAs have read it
-            for (int t = 0; t < 4; ++t) { mbar_init(&sm.acc_full[t >> 1][t & 1], 1); sm.acc_arrivals[t >> 1][t & 1] = 0u; }
+            for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 1); }
+            for (int t = 0; t < 2; ++t) { mbar_init(&sm.acc_full[t], 1); mbar_init(&sm.acc_empty[t], RS_WARPS); }     // every epilogue warp hands the buffer back
             mbar_fence_init();
+            sm.tc_ntiles = 0;
         }
-        if (warp == 0) tmem_alloc512(&sm.tmem_base);
-        for (int i = threadIdx.x; i < (int)sizeof(sm.u.tc.b_op) / 16; i += RS_THREADS) reinterpret_cast<uint4*>(sm.u.tc.b_op)[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (warp == RS_WARPS) tmem_alloc512(&sm.tmem_base);
+        for (int i = threadIdx.x; i < (int)sizeof(sm.u.tc.b_op) / 16; i += RS_LAUNCH) reinterpret_cast<uint4*>(sm.u.tc.b_op)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x < 4) sm.stat[threadIdx.x] = 0u;
+        fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+    }
+    if (warp == RS_WARPS) {                                           // the tensor-core warp
+        if (tc_on) {
+            tc_warp_loop(sm, tc_scratch + (size_t)blockIdx.x * RT_MAX_TILES * RT_TILE_BYTES);
+            tc_fence_before();
+            __syncwarp();
+            tmem_dealloc512(sm.tmem_base);
+        }
+        return;
     }
 
     RsTc tc;
@@ -835,10 +836,10 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
             if (b) atomicMax(best_packed + p, b);
         }
     }
-    if (tc_on) {
-        tc_fence_before();
-        __syncthreads();
-        if (warp == 0) tmem_dealloc512(sm.tmem_base);
+    if (tc_on) {                                                      // release the tensor-core warp
+        rs_sync();
+        if (threadIdx.x == 0) sm.tc_ntiles = -1;
+        rs_sync_all();
     }
 #ifdef RS_TIMING
     if (threadIdx.x == 0) {
@@ -1156,7 +1157,7 @@ cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int3
     unsigned char* scratch = reinterpret_cast<unsigned char*>(((uintptr_t)tc_scratch + 15) & ~(uintptr_t)15);
     if (!tc_scratch || g_ransac_tc == 0 || (size_t)(scratch - reinterpret_cast<unsigned char*>(tc_scratch)) + (size_t)grid * RT_MAX_TILES * RT_TILE_BYTES > tc_scratch_bytes)
         scratch = nullptr;
-    ransac_kernel<<<grid, RS_THREADS, smem, stream>>>(reinterpret_cast<const float4*>(corr), corr_off, corr_cnt, P, splits, seed, pair_id_base,
+    ransac_kernel<<<grid, RS_LAUNCH, smem, stream>>>(reinterpret_cast<const float4*>(corr), corr_off, corr_cnt, P, splits, seed, pair_id_base,
                                                      h_begin, h_end, dist_th, similar_th, confidence, best_packed, valid_count, scratch);
     return cudaGetLastError();
 }

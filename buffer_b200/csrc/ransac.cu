@@ -33,7 +33,7 @@
 
 namespace bfr {
 
-constexpr int RS_THREADS = 384;                 // worker threads: stage 1, fits, scoring / tensor-core epilogue
+constexpr int RS_THREADS = 512;                 // worker threads: stage 1, fits, scoring / tensor-core epilogue
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_LAUNCH = RS_THREADS + 32;      // + the warp that feeds the tensor core (TMA of the A tiles, tcgen05.mma issue): 13 warps, <= 152 registers
 constexpr int RS_CHUNK = 5120;                  // correspondences per shared-memory chunk; pairs with K <= RS_CHUNK stay resident
@@ -55,6 +55,7 @@ constexpr int RT_TILE = 128;                    // correspondences per A tile (M
 constexpr int RT_TILE_BYTES = RT_TILE * 32;     // K = 16 f16 per row
 constexpr int RT_STAGES = 8;                    // A tiles in flight (TMA ring): the MMAs run two tiles ahead of the epilogue, the copies five more
 constexpr int RT_MAX_TILES = RS_CHUNK / RT_TILE;
+constexpr int RT_MIN_TC = 48;                    // smaller flushes (the tail of an item) are cheaper on the exact FP32 loop than 40 tile hand-offs
 constexpr float RT_RANGE = 8192.0f;             // largest |s|_1, |q_i|, |t_i| the f16 splits are used for (beyond: exact FP32 scoring)
 constexpr float RT_PAD_Q = 32768.0f;            // target coordinate of the padding rows of the last A tile: never an inlier, never in the band
 
@@ -453,7 +454,7 @@ __device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d
     const float delta = 1.02f * 2.1457672e-6f * bp;
     const float rt = sqrtf(d2max);
     const float band = 1.02f * (delta * (4.8989795f * rt + 3.0f * delta) + 9.5367432e-7f * d2max);
-    const bool ok = !fallback && delta <= 0.015625f * rt && d2max > 0.0f && d2max <= 1.0e6f;
+    const bool ok = !fallback && n >= RT_MIN_TC && delta <= 0.015625f * rt && d2max > 0.0f && d2max <= 1.0e6f;
     if (!ok) {                                  // block-uniform: score these hypotheses exactly
         rs_sync();
         if (threadIdx.x == 0) { sm.stat[2] = 0u; sm.stat[3] = 0u; }

@@ -575,3 +575,80 @@ def test_tensor_filter_equals_fp32_kernel_on_stress_inputs(backend):
                 assert torch.equal(out[backend.K1_FP32][key], out[backend.K1_TENSOR_FILTER][key]), (kind, M, N, key)
     finally:
         backend.set_k1_algo(backend.K1_TENSOR_FILTER)
+
+
+def _ransac_both_ways(backend, corr, H, dist_th=0.1, sim_th=0.8, splits=1, seed=3):
+    K = corr.shape[0]
+    off = torch.tensor([0, K], dtype=torch.int32, device=DEV); cnt = torch.tensor([K], dtype=torch.int32, device=DEV)
+    out = []
+    try:
+        for algo in (backend.RANSAC_TENSOR_FILTER, backend.RANSAC_FP32):
+            backend.set_ransac_scoring(algo)
+            nv = torch.zeros(1, dtype=torch.int32, device=DEV)
+            bp = backend.ransac_batched(corr.to(DEV), off, cnt, H, dist_th, sim_th, seed=seed, pair_id_base=11, splits=splits, valid_count=nv)
+            out.append((int(bp.item()), int(nv.item())))
+    finally:
+        backend.set_ransac_scoring(backend.RANSAC_TENSOR_FILTER)
+    return out
+
+
+@pytest.mark.parametrize("K", [3, 100, 127, 128, 129, 1000, 5119, 5120, 5121])
+def test_ransac_tensor_filter_equals_fp32_scoring(oracle, backend, K):
+    """RANSAC scores hypotheses either with the exact FP32 loop or with the tcgen05 residual filter (2-level f16 operand splits) + exact
+    re-check of the residuals inside the error band: both must return the same packed best and the same number of valid hypotheses, and
+    equal the oracle.  K straddles the 128-correspondence A tiles and the 5120-correspondence residency limit (beyond: FP32 only)."""
+    g = torch.Generator().manual_seed(K)
+    s = torch.rand(K, 3, generator=g) * 3 - 1.5
+    q = s + 0.03 * torch.randn(K, 3, generator=g)
+    out = torch.rand(K, generator=g) < 0.5
+    q[out] = torch.rand(int(out.sum()), 3, generator=g) * 3 - 1.5
+    rec = torch.zeros(K, 8); rec[:, :3] = s; rec[:, 4:7] = q
+    (b1, n1), (b0, n0) = _ransac_both_ways(backend, rec, 6000)
+    assert (b1, n1) == (b0, n0)
+    assert b1 == oracle.ransac(rec.numpy(), 3, 11, 6000, 0.1, 0.8)
+
+
+def test_ransac_tensor_filter_adversarial(oracle, backend):
+    """inputs built to sit on the filter's decision boundary or outside its operating range"""
+    g = torch.Generator().manual_seed(77)
+    K = 2000
+    s = torch.rand(K, 3, generator=g) * 2 - 1
+    q = s.clone(); q[:, 0] += 0.1                                     # residual == threshold under the identity ...
+    q[::3, 0] = torch.nextafter(q[::3, 0], torch.tensor(10.0)); q[1::3, 0] = torch.nextafter(q[1::3, 0], torch.tensor(-10.0))    # ... +- 1 ulp
+    q[:600] = s[:600]
+    rec = torch.zeros(K, 8); rec[:, :3] = s; rec[:, 4:7] = q
+    cases = [("on the threshold", rec, 0.1)]
+    far = rec.clone(); far[:, :3] += 20000.0; far[:, 4:7] += 20000.0  # beyond the f16 split range: the pair is scored in FP32
+    cases.append(("coordinates 2e4", far, 0.1))
+    big = rec.clone(); big[:, :3] *= 100.0; big[:, 4:7] *= 100.0
+    cases.append(("coordinates 100, threshold 10", big, 10.0))
+    tiny = rec.clone(); tiny[:, :3] *= 1e-3; tiny[:, 4:7] *= 1e-3
+    cases.append(("coordinates 1e-3, threshold 1e-4", tiny, 1e-4))
+    nan = rec.clone(); nan[17, 5] = float("nan")
+    cases.append(("one NaN coordinate", nan, 0.1))
+    for name, r, thr in cases:
+        for splits in (1, 3):
+            (b1, n1), (b0, n0) = _ransac_both_ways(backend, r, 5000, dist_th=thr, splits=splits)
+            assert (b1, n1) == (b0, n0), name
+        if name != "one NaN coordinate":
+            assert b1 == oracle.ransac(r.numpy(), 3, 11, 5000, thr, 0.8), name
+
+
+def test_ransac_tensor_filter_full_size_pairs(backend):
+    """config-2-sized pairs (5000 correspondences, 50000 hypotheses): the two scoring paths agree on every pair of a batch"""
+    b = _pairs(6, 5000, cfg_id=2)
+    P, N = 6, 5000
+    off = (torch.arange(P + 1, dtype=torch.int32) * N).to(DEV)
+    rm = backend.mutual_matching_batched(b.src_des.reshape(P * N, 32).to(DEV), b.tgt_des.reshape(P * N, 32).to(DEV), off, off, N, N,
+                                         b.src_xyz.reshape(P * N, 3).to(DEV), b.tgt_xyz.reshape(P * N, 3).to(DEV), want_nn=False, want_mids=False)
+    res = []
+    try:
+        for algo in (backend.RANSAC_TENSOR_FILTER, backend.RANSAC_FP32):
+            backend.set_ransac_scoring(algo)
+            nv = torch.zeros(P, dtype=torch.int32, device=DEV)
+            bp = backend.ransac_batched(rm["corr"], off, rm["n_mutual"], 50000, 0.1, 0.8, seed=1, pair_id_base=0, splits=2, valid_count=nv)
+            res.append((bp.clone(), nv.clone()))
+    finally:
+        backend.set_ransac_scoring(backend.RANSAC_TENSOR_FILTER)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    assert int(res[0][0].min().item()) >> 32 > 1000

@@ -70,6 +70,11 @@ def test_c_abi_exports_every_declared_symbol():
     assert L.bfr_mutual_matching_batched(None, None, None, None, 1, 1, 1, 1, 1, 32, 1, None, None, None, None, None, None, None, None, None, None, None, 0, None) == -1
     assert L.bfr_ransac_batched(None, None, None, 0, 0, 0, 0, 0, 0.1, 0.8, 1.0, 1, None, None, None, 0, None) == 0     # P == 0 is a no-op
     assert L.bfr_rigid_transform_3d(None, None, None, 3, 3, 0.0, None, None) == -1
+    # RANSAC scratch for the tensor-core scoring filter: one 4 KB A tile per 128 correspondences, 40 tiles per resident pair, per CTA
+    assert L.bfr_ransac_workspace_bytes() >= 148 * 40 * 4096
+    assert L.bfr_register_workspace_bytes(2, 100, 100, 200, 200) >= L.bfr_ransac_workspace_bytes()
+    assert L.bfr_config_get(2) == 1 and L.bfr_config_set(2, 0) == 0 and L.bfr_config_get(2) == 0 and L.bfr_config_set(2, 1) == 0
+    assert L.bfr_config_set(2, 7) == -2 and L.bfr_config_set(99, 0) == -2
     # more than BFR_MAX_PAIRS pairs in one call is an argument error (BFR_E_SIZE), reported before anything touches the device
     buf = ctypes.create_string_buffer(64)
     ptr = ctypes.cast(buf, ctypes.c_void_p)

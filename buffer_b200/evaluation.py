@@ -71,57 +71,59 @@ def read_trajectory_info(filename, dim=6):
     return n_frame, np.asarray(info, dtype=np.float32).reshape(-1, dim, dim)
 
 
+def _error_vectors(trans):
+    """[n,4,4] -> [n,6] rows (tx, ty, tz, qx, qy, qz): translation and vector part of the rotation quaternion"""
+    trans = np.asarray(trans, dtype=np.float64).reshape(-1, 4, 4)
+    quat_xyz = np.stack([mat2quat(T[:3, :3])[1:] for T in trans]) if len(trans) else np.zeros((0, 3))
+    return np.concatenate([trans[:, :3, 3], quat_xyz], axis=1)
+
+
+def _information_errors(trans, info):
+    """batched quadratic form ``e^T I e / I[0,0]`` with ``e = _error_vectors(trans)``; trans [n,4,4], info [n,6,6] -> [n]"""
+    e = _error_vectors(trans)
+    info = np.asarray(info, dtype=np.float64).reshape(-1, 6, 6)
+    return np.einsum("ni,nij,nj->n", e, info, e) / info[:, 0, 0]
+
+
 def computeTransformationErr(trans, info):
-    """``e = [t, q_xyz]`` of the 4x4 ``trans``; returns ``e^T info e / info[0,0]`` (ThreeDMatch/test.py:92-110)."""
-    t = trans[:3, 3]
-    q = mat2quat(trans[:3, :3])
-    er = np.concatenate([t, q[1:]], axis=0)
-    p = er.reshape(1, 6) @ info @ er.reshape(6, 1) / info[0, 0]
-    return p.item()
+    """``e^T info e / info[0,0]`` for the 6-vector ``e`` = (translation, quaternion xyz) of the 4x4 ``trans`` (ThreeDMatch/test.py:92-110)."""
+    return float(_information_errors(np.asarray(trans)[None], np.asarray(info)[None])[0])
 
 
 def evaluate_registration(num_fragment, result, result_pairs, gt_pairs, gt, gt_info, err2=0.2):
     """3DMatch / Redwood protocol (ThreeDMatch/test.py:113-173): only non-consecutive ground-truth pairs count; an estimate is good when
-    ``computeTransformationErr(inv(gt) @ pose, info) <= err2**2``.  Returns (precision, recall, flags, transformation_errors);
+    the information-weighted error of ``inv(gt) @ pose`` is at most ``err2**2``.  Returns (precision, recall, flags, transformation_errors);
     flags: 0 good, 1 wrong, 2 pair not in the ground truth.  Like the reference, ground-truth entry 0 can never be hit (its index doubles as
-    the "no pair" marker of the mask)."""
-    err2 = err2 ** 2
-    gt_mask = np.zeros((num_fragment, num_fragment), dtype=np.int64)
-    for idx in range(gt_pairs.shape[0]):
-        i, j = int(gt_pairs[idx, 0]), int(gt_pairs[idx, 1])
-        if j - i > 1:
-            gt_mask[i, j] = idx
-    n_gt = np.sum(gt_mask > 0)
-    transformation_errors = np.full(result_pairs.shape[0], np.nan)
-    flags, good, n_res = [], 0, 0
-    for idx in range(result_pairs.shape[0]):
-        i, j = int(result_pairs[idx, 0]), int(result_pairs[idx, 1])
-        if gt_mask[i, j] > 0:
-            n_res += 1
-            g = gt_mask[i, j]
-            p = computeTransformationErr(np.linalg.inv(gt[g, :, :]) @ result[idx, :, :], gt_info[g, :, :])
-            transformation_errors[idx] = p
-            if p <= err2:
-                good += 1
-                flags.append(0)
-            else:
-                flags.append(1)
-        else:
-            flags.append(2)
-    if n_res == 0:
-        n_res += 1e6
-    return good * 1.0 / n_res, good * 1.0 / n_gt, flags, transformation_errors
+    the "no pair" marker of the lookup table).  Vectorised: one table lookup for all estimates, one batched quadratic form."""
+    gt_pairs = np.asarray(gt_pairs); result_pairs = np.asarray(result_pairs)
+    gi, gj = gt_pairs[:, 0].astype(np.int64), gt_pairs[:, 1].astype(np.int64)
+    far = (gj - gi) > 1
+    lookup = np.zeros((num_fragment, num_fragment), dtype=np.int64)
+    lookup[gi[far], gj[far]] = np.nonzero(far)[0]                    # later duplicates overwrite earlier ones, as a sequential fill would
+    ri, rj = result_pairs[:, 0].astype(np.int64), result_pairs[:, 1].astype(np.int64)
+    hit = lookup[ri, rj]                                              # ground-truth row of every estimate, 0 = not evaluated
+    known = hit > 0
+    errors = np.full(len(result_pairs), np.nan)
+    if known.any():
+        rel = np.linalg.inv(np.asarray(gt)[hit[known]]) @ np.asarray(result)[known]      # in the trajectories' own dtype (float32 from the readers), like the reference
+        errors[known] = _information_errors(rel, np.asarray(gt_info)[hit[known]])
+    ok = known & (errors <= err2 ** 2)
+    flags = np.where(ok, 0, np.where(known, 1, 2)).tolist()
+    evaluated = int(known.sum()) if known.any() else 1e6
+    return ok.sum() * 1.0 / evaluated, ok.sum() * 1.0 / np.count_nonzero(lookup), flags, errors
 
 
 def extract_corresponding_trajectors(est_pairs, gt_pairs, gt_traj):
     """ground-truth transforms of exactly the estimated pairs (ThreeDMatch/test.py:176-197); like the reference it overwrites the third
-    column of ``est_pairs`` with the scene's fragment count."""
-    ext_traj = np.zeros((len(est_pairs), 4, 4))
-    for est_idx, pair in enumerate(est_pairs):
-        pair[2] = gt_pairs[0][2]
-        gt_idx = np.where((gt_pairs == pair).all(axis=1))[0]
-        ext_traj[est_idx, :, :] = gt_traj[gt_idx, :, :]
-    return ext_traj
+    column of ``est_pairs`` with the scene's fragment count.  One broadcast comparison instead of a search per pair; an estimated pair
+    without a ground-truth row keeps a zero matrix."""
+    gt_pairs = np.asarray(gt_pairs)
+    est_pairs[:, 2] = gt_pairs[0][2]
+    same = (np.asarray(est_pairs)[:, None, :] == gt_pairs[None, :, :]).all(axis=2)          # [n_est, n_gt]
+    out = np.zeros((len(est_pairs), 4, 4))
+    found = same.any(axis=1)
+    out[found] = np.asarray(gt_traj)[same.argmax(axis=1)[found]]
+    return out
 
 
 def write_trajectory_entry(path, src_id, tgt_id, trans_est):

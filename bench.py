@@ -397,6 +397,19 @@ def main():
             ransac_ms.append(ea.elapsed_time(eb))
         ransac_ms = min(ransac_ms)
         hv_total = float(nvalid.sum().item()); c_mean = float(rm["n_mutual"].float().mean().item())
+        # same launch with every residual in FP32 (BFR_CFG_RANSAC_TC = 0): the two scoring paths must return identical packed bests
+        bp_tc = B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], seed=0, pair_id_base=p_lo).clone()
+        B.set_ransac_scoring(B.RANSAC_FP32)
+        ransac_fp32_ms = []
+        for i in range(3):
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record()
+            bp_fp = B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], seed=0, pair_id_base=p_lo)
+            eb.record(); eb.synchronize()
+            ransac_fp32_ms.append(ea.elapsed_time(eb))
+        B.set_ransac_scoring(B.RANSAC_TENSOR_FILTER)
+        ransac_fp32_ms = min(ransac_fp32_ms)
+        ransac_same = bool(torch.equal(bp_tc, bp_fp))
         # Open3D's confidence early exit (the reference's 3DMatch setting, ThreeDMatch/config.py:65): same call with confidence = 0.999
         conf_ms = []
         for i in range(3):
@@ -506,14 +519,17 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, c, P_total, world), "clocks": clocks, "gpu_launches": 8 * args.steps,
                 "roofline": roof, "roofline_fp32_path": fp32_roof,
-                "roofline_ransac": {"kernel": "ransac_kernel (Philox + Kabsch + checkers + inlier scoring)", "bound": "fp32", "ms_per_launch": ransac_ms,
+                "roofline_ransac": {"kernel": "ransac_kernel (Philox + Kabsch + checkers + inlier scoring: tcgen05 residual filter on 2-level f16 operand splits, exact FP32 re-check inside the error band)",
+                                    "bound": "fp32", "ms_per_launch": ransac_ms, "ms_per_launch_fp32_scoring": ransac_fp32_ms, "outputs_identical_to_fp32_scoring": ransac_same,
                                     "valid_hypotheses_per_pair": hv_total / P, "hypotheses_per_pair": c["hypotheses"], "correspondences_per_pair": c_mean,
                                     "algorithmic_flops_per_launch": 28.0 * hv_total * c_mean, "achieved": 28.0 * hv_total * c_mean / (ransac_ms * 1e-3) * 1e-12,
                                     "peak": peak_tf, "unit": "TFLOP/s", "frac": 28.0 * hv_total * c_mean / (ransac_ms * 1e-3) * 1e-12 / peak_tf,
                                     "hypotheses_per_s": P * c["hypotheses"] / (ransac_ms * 1e-3),
                                     "streaming_model_gbs": 24.0 * c_mean * hv_total / 512.0 / (ransac_ms * 1e-3) * 1e-9,
-                                    "streaming_model_note": "bytes = 24*C*H_valid/T_h with T_h = 512 hypotheses per CTA pass; a pair's correspondences are loaded ONCE into shared memory "
-                                                            "(compulsory HBM traffic is 32*C bytes per pair), so the kernel is FP32-issue-bound, not HBM-bound",
+                                    "streaming_model_note": "bytes = 24*C*H_valid/T_h with T_h = 512 hypotheses per CTA pass (the all-FP32 formulation); a pair's correspondences are loaded ONCE "
+                                                            "into shared memory (compulsory HBM traffic is 32*C bytes per pair), so the kernel is issue-bound, not HBM-bound",
+                                    "note": "achieved/frac count the 28 flop per (hypothesis, correspondence) of the FP32 formulation; with the tensor-core filter 19 of them run as tcgen05.mma "
+                                            "and the kernel is bound by the accumulator hand-off per 128-correspondence tile (DESIGN.md K2+K3)",
                                     "open3d_confidence_exit": conf},
                 "quality": {"registration_recall": recall, "rte_max_m": qmax[0].item(), "rre_max_deg": qmax[1].item(),
                             "mutual_matches_mean": float(nm.float().mean()), "ransac_inliers_mean": float(ni.float().mean())}}

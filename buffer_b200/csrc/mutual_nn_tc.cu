@@ -19,7 +19,7 @@
 //
 // Warp roles (320 threads, 1 CTA/SM, 256 own rows = 2 row halves, 512 TMEM columns = one 128 x 256 accumulator tile per half):
 //   warp 0   TMA producer: the CTA's 256 "own" rows once, then 256-row tiles of the streamed side through a 3-stage ring
-//            (cp.async.bulk.tensor.2d, two K = 16 planes per tile, SWIZZLE_32B, mbarrier expect-tx)
+//            (cp.async.bulk.tensor.2d, SWIZZLE_64B, mbarrier expect-tx)
 //   warp 1   TMEM allocator + MMA issuer: per tile and half 2 x tcgen05.mma (K = 2 x 16), tcgen05.commit -> accumulator full / stage free
 //   warps 2-9 epilogue (one thread per own row): two batches of 4 x tcgen05.ld.32x32b.x32, (add hn(b_j),) FMNMX3 tree per 4-column
 //            group, predicated append of the chunks inside the band; the tile goes back to the MMA warp as soon as the second
@@ -53,8 +53,8 @@ __device__ unsigned long long g_dbg[8];
 #endif
 
 struct TcSmem {
-    uint16_t a[TC_BM * TC_D];                   // 16 KB f16: two K = 16 planes (dims 0-15 | 16-31) of 256 rows x 32 bytes, SWIZZLE_32B K-major; rows 128.. of a plane = second half
-    uint16_t b[TC_STAGES][TC_BN * TC_D];        // 3 x 16 KB, same two-plane layout (after the last MMA: uint32_t glist[TC_GCAP][TC_BM], the groups to re-check)
+    uint16_t a[TC_BM * TC_D];                   // 16 KB f16, SWIZZLE_64B K-major (one 64-byte row per descriptor); rows 128.. = second half
+    uint16_t b[TC_STAGES][TC_BN * TC_D];        // 3 x 16 KB (after the last MMA: uint32_t glist[TC_GCAP][TC_BM], the groups to re-check)
     float hn[TC_MAX_TILES * TC_BN];             // -|b_j|^2/2 of the CTA's streamed columns (-inf beyond the pair)
     struct Ev {                                 // band events of one epilogue warp (once consumed: the warp's 16 KB staging area of the re-check)
         float4 cmg[TC_CAP][2][32];              //   [slot][half][lane]: the eight 4-column group maxima of the chunk
@@ -99,14 +99,10 @@ BFR_DEVINL void l2_prefetch(const void* gptr, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
-// Operand tiles are K = 16 planes with 32-byte rows: an MMA then reads whole rows.  With one 64-byte row per descriptor (SWIZZLE_64B) each
-// K = 16 instruction touched half of every row and the operand fetch, not the tensor pipe, set the pace (2 MMAs per accumulator tile:
-// ~580 cycles against ~256, tools/microbench/mma_bubble.cu vs rs_mma.cu).
-BFR_DEVINL uint64_t umma_desc_sw32(const void* smem)
-{   // K-major, SWIZZLE_32B: 8-row groups 256 B apart (SBO = 16 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell), layout 6 = SW32
-    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (16ull << 32) | (1ull << 46) | (6ull << 61);
+BFR_DEVINL uint64_t umma_desc_sw64(const void* smem)
+{   // K-major, SWIZZLE_64B: 8-row groups 512 B apart (SBO = 32 x 16 B), LBO ignored (1), descriptor version 1 (Blackwell), layout 4 = SW64
+    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
 }
-constexpr int TC_PLANE_A = TC_BM * 16, TC_PLANE_B = TC_BN * 16;     // f16 elements per K = 16 plane
 // exact score of (own row, candidate row) — the oracle's chain.  COLDIR = the "own" side is the target set.
 BFR_DEVINL float exact_score(bool COLDIR, const float4 (&own)[8], float own_hn, const float* __restrict__ cand_row, float cand_hn)
 {
@@ -301,7 +297,6 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
         if (lane == 0) {
             mbar_expect_tx(&sm.a_full, TC_BM * TC_D * 2);
             tma_load_2d(sm.a, map_own, 0, oo + row0, &sm.a_full);
-            tma_load_2d(sm.a + TC_PLANE_A, map_own, 16, oo + row0, &sm.a_full);
 #ifndef TC_NO_L2_PREFETCH
             // The exact re-check reads FP32 rows the main loop never touches (it streams the f16 copies): the CTA's own rows and a
             // scattered subset of the streamed set.  Pull them towards L2 now - the own rows, and this CTA's share of the streamed rows of
@@ -320,7 +315,6 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
                 mbar_wait(&sm.empty[s], ph ^ 1u);
                 mbar_expect_tx(&sm.full[s], TC_BN * TC_D * 2);
                 tma_load_2d(sm.b[s], map_str, 0, os + (t_begin + it) * TC_BN, &sm.full[s]);
-                tma_load_2d(sm.b[s] + TC_PLANE_B, map_str, 16, os + (t_begin + it) * TC_BN, &sm.full[s]);
             }
         }
     } else if (warp == 1) {
@@ -328,20 +322,20 @@ k1_tc_kernel(const __grid_constant__ CUtensorMap map_src_own, const __grid_const
         if (lane == 0) {
             // instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 256, M = 128
             const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint64_t adesc0 = umma_desc_sw32(sm.a), adesc1 = umma_desc_sw32(sm.a + 128 * 16);             // plane 0 of the two row halves
+            const uint64_t adesc0 = umma_desc_sw64(sm.a), adesc1 = umma_desc_sw64(sm.a + 128 * TC_D);
             mbar_wait(&sm.a_full, 0);
             for (int it = 0; it < ntiles; ++it) {
                 const int s = it % TC_STAGES; const uint32_t ph = (uint32_t)(it / TC_STAGES) & 1u;
                 mbar_wait(&sm.full[s], ph);
-                const uint64_t bdesc = umma_desc_sw32(sm.b[s]);
+                const uint64_t bdesc = umma_desc_sw64(sm.b[s]);
                 for (int h = 0; h < halves; ++h) {                    // one accumulator tile (128 rows x 256 streamed columns) per row half
                     mbar_wait(&sm.acc_empty[h], ((uint32_t)it & 1u) ^ 1u);
                     tc_fence_after();
                     const uint32_t d = tmem_base + (uint32_t)(h * TC_BN);
                     const uint64_t ad = h ? adesc1 : adesc0;
 #pragma unroll
-                    for (int k = 0; k < TC_MMAK; ++k)              // K = 16 per instruction: plane k of both operands
-                        umma_f16(d, ad + (uint64_t)(k * (TC_PLANE_A * 2 >> 4)), bdesc + (uint64_t)(k * (TC_PLANE_B * 2 >> 4)), idesc, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < TC_MMAK; ++k)              // K = 16 per instruction: +32 bytes (2 x 16 B) per step inside the 64-byte row
+                        umma_f16(d, ad + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k > 0 ? 1u : 0u);
                     umma_commit(&sm.acc_full[h]);
                 }
                 umma_commit(&sm.empty[s]);                            // the stage is free once every MMA that reads it has completed
@@ -644,10 +638,10 @@ static bool make_map(CUtensorMap* map, const void* base, long long rows, int box
     if (!fn) return false;
     cuuint64_t dims[2] = { (cuuint64_t)TC_D, (cuuint64_t)rows };
     cuuint64_t strides[1] = { (cuuint64_t)TC_D * 2 };
-    cuuint32_t box[2] = { 16u, (cuuint32_t)box_rows };                  // one K = 16 plane (32 bytes of every 64-byte row) per copy
+    cuuint32_t box[2] = { (cuuint32_t)TC_D, (cuuint32_t)box_rows };
     cuuint32_t estr[2] = { 1, 1 };
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool k1_tc_supported(int D, long long total_M, long long total_N) { return D == TC_D && total_M > 0 && total_N > 0 && encode_fn() != nullptr; }

@@ -42,7 +42,7 @@ constexpr int RS_CHUNK = 5120;                  // correspondences per shared-me
 #endif
 constexpr int RS_S1 = RS_S1_N;                     // stage-1 hypotheses per thread and round
 constexpr int RS_QCAP = 2 * RS_THREADS;            // queue 2 (exact scoring): < RS_THREADS leftovers plus the survivors of one fit block
-constexpr int RS_Q1CAP = (1 + RS_S1) * RS_THREADS; // queue 1 holds < RS_THREADS leftovers plus one round's survivors (hypothesis index only)
+constexpr int RS_Q1CAP = ((1 + RS_S1) > 5 ? (1 + RS_S1) : 5) * RS_THREADS; // queue 1 holds < RS_THREADS leftovers plus one round's survivors (hypothesis index only)
 constexpr int RS_MAX_CTAS = 160;                   // upper bound of the persistent grid (sizes the tensor-core scratch)
 
 // tensor-core scoring filter
@@ -105,7 +105,7 @@ struct __align__(1024) RsSmem {
 #endif
     uint32_t stat[4];                           // float bits: max |s|_1, max |q_i| of the pair, max |t_i| of the flush; [3] != 0: out of range / non-finite
 };
-static_assert(sizeof(RsSmem) + 1024 <= 227 * 1024, "RsSmem must fit one CTA's shared memory");
+static_assert(sizeof(RsSmem) <= 227 * 1024, "RsSmem must fit one CTA's shared memory");
 static_assert(RS_Q1CAP >= 5 * RS_THREADS, "queue 1 doubles as partial counts + round results of the confidence mode");
 static_assert(RT_TILE_BYTES >= 2 * RS_THREADS * (int)sizeof(int), "an A-ring stage doubles as scratch of the exact fallback of a flush");
 static_assert(offsetof(RsSmem, u) % 1024 == 0, "operand tiles start on a 1 KB boundary");
@@ -117,6 +117,10 @@ struct __align__(16) ScSmem {
     float4 chunk[SC_CHUNK / 2][4];              // ... + (w w' - -): per-correspondence squared-distance thresholds
     unsigned long long red[SC_THREADS / 32];
 };
+
+// the kernel's shared memory, re-derived from the symbol so that out-of-line functions keep shared-state-space loads and stores too
+extern __shared__ __align__(1024) unsigned char rs_smem_raw[];
+BFR_DEVINL RsSmem& rs_smem() { return *reinterpret_cast<RsSmem*>(rs_smem_raw); }
 
 // barrier of the worker threads (the tensor-core warp is not part of it) / of all threads (hands a flush to the tensor-core warp)
 BFR_DEVINL void rs_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RS_THREADS) : "memory"); }
@@ -377,8 +381,9 @@ BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scrat
 // Out of line (rare): correspondence c against the (up to) 10 hypotheses of one chunk, queue entries qbase .. qbase + 9 (the first
 // `nvalid` exist); w[k] = approximate d2 - d2max.  Every pair inside the band is re-evaluated with the oracle's FP32 chain.
 // Returns bit k: exact says inlier but the filter said no; bit 16 + k: the filter said inlier but exact says no.
-__device__ __noinline__ uint32_t tc_recheck(const RsSmem& sm, uint32_t c, int qbase, int nvalid, float d2max, float band, const float (&w)[10])
+__device__ __noinline__ uint32_t tc_recheck(uint32_t c, int qbase, int nvalid, float d2max, float band, const float (&w)[10])
 {
+    const RsSmem& sm = rs_smem();
     float s[3], q[3];
     load_record_smem(sm, c, s, q);
     uint32_t fix = 0u;
@@ -409,8 +414,9 @@ __device__ __noinline__ uint32_t tc_recheck(const RsSmem& sm, uint32_t c, int qb
 // `tile0` = A tiles consumed before this flush (the mbarrier phase clock).
 // Returns, in threads < n, the exact inlier count of hypothesis base + threadIdx.x; bit 30 is set (in every thread) if the tensor-core path
 // ran, i.e. ceil(K / 128) A tiles were consumed.  Out of line: ransac_item flushes from three places.
-__device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d2max, float s1max, float qmax, const unsigned char* __restrict__ scratch, uint32_t tile0)
+__device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float s1max, float qmax, uint32_t tile0)
 {
+    RsSmem& sm = rs_smem();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #ifdef RS_TRACE
     const bool trace_on = blockIdx.x == 0 && tile0 >= 80u && tile0 < 120u;
@@ -501,7 +507,7 @@ __device__ __noinline__ int tc_flush(RsSmem& sm, int K, int base, int n, float d
                     const f32x2 x = pack2(v[6 * pr], v[6 * pr + 1]), y = pack2(v[6 * pr + 2], v[6 * pr + 3]), z = pack2(v[6 * pr + 4], v[6 * pr + 5]);
                     unpack2(fma2(x, x, fma2(y, y, fma2(z, z, negT))), w[2 * pr], w[2 * pr + 1]);
                 }
-                const uint32_t fix = tc_recheck(sm, (uint32_t)c, base + hl0 + ch * 10, n - (hl0 + ch * 10), d2max, band, w);
+                const uint32_t fix = tc_recheck((uint32_t)c, base + hl0 + ch * 10, n - (hl0 + ch * 10), d2max, band, w);
 #pragma unroll
                 for (int k = 0; k < 10; ++k) c10[k] += (int)((fix >> k) & 1u) - (int)((fix >> (16 + k)) & 1u);
             }
@@ -617,7 +623,7 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
                 const int base = qn - n;
                 if (TC) {
                     int count;
-                    RST(tm[2], count = tc_flush(sm, K, base, n, d2max, tc.s1max, tc.qmax, tc.scratch, tc.tile0));
+                    RST(tm[2], count = tc_flush(K, base, n, d2max, tc.s1max, tc.qmax, tc.tile0));
                     if (count & (1 << 30)) { tc.tile0 += (uint32_t)((K + RT_TILE - 1) / RT_TILE); count &= ~(1 << 30); }
                     if ((int)threadIdx.x < n) { const unsigned long long pk = pack_count(count, sm.u.tc.qh[base + threadIdx.x]); best = pk > best ? pk : best; }
                 } else {
@@ -756,8 +762,8 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
               uint64_t seed, uint32_t pair_id_base, uint32_t h_begin, uint32_t h_end, float dist_th, float similar_th, float confidence,
               unsigned long long* __restrict__ best_packed, int32_t* __restrict__ valid_count, unsigned char* __restrict__ tc_scratch)
 {
-    extern __shared__ unsigned char smem_raw[];
-    RsSmem& sm = *reinterpret_cast<RsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    RsSmem& sm = rs_smem();                                           // no static shared memory in this kernel: the dynamic base is 1024-aligned (no integer
+    if ((smem_u32(&sm) & 127u) != 0u) __trap();                       // round-up of the pointer: it would turn every access into a generic load)
     const float d2max = __fmul_rn(dist_th, dist_th), sim2 = __fmul_rn(similar_th, similar_th);
     const bool conf = confidence > 0.0f && confidence < 1.0f;
     const bool tc_on = tc_scratch != nullptr && !conf;                // kernel-uniform: the tensor-core warp serves this launch
@@ -1145,7 +1151,7 @@ cudaError_t ransac_launch(const float* corr, const int32_t* corr_off, const int3
                           unsigned long long* best_packed, int32_t* valid_count, void* tc_scratch, size_t tc_scratch_bytes, cudaStream_t stream)
 {
     static std::atomic<unsigned long long> attr_done{0};
-    const size_t smem = sizeof(RsSmem) + 1024;
+    const size_t smem = sizeof(RsSmem);
     cudaError_t e = ensure_dyn_smem((const void*)ransac_kernel, (int)smem, attr_done);
     if (e != cudaSuccess) return e;
     if (P <= 0 || h_end <= h_begin) return cudaSuccess;

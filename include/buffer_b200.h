@@ -11,7 +11,7 @@
  *  - Every pointer is a DEVICE pointer unless the name ends in _host.  The caller owns all memory including the
  *    workspace (`ws`, size from the matching *_workspace_bytes); the library never allocates device memory and every
  *    call is asynchronous on `stream` (no host sync inside) unless stated.  State kept by the library: the per-THREAD
- *    tuning knob of bfr_config_set / the per-thread debug events (each host thread sees only its own), and one
+ *    tuning knobs of bfr_config_set / the per-thread debug events (each host thread sees only its own), and one
  *    "shared-memory opt-in done" bit per kernel and device ordinal (idempotent) - calls from several host threads
  *    and on several devices of one process are safe.  Launches go to the CURRENT device of the calling thread: make
  *    the device that owns the buffers current before calling.

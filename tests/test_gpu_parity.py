@@ -1,6 +1,8 @@
 """GPU parity tests proper: every result of the CUDA path (through the C ABI) against the CPU oracle on the same
 seeded inputs.  Integer / index / count outputs must be bit-exact; transforms are compared bit-for-bit where the
 arithmetic order is pinned (RANSAC fit, refinement) and within 1e-5 against float64 ground truth otherwise."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -652,3 +654,26 @@ def test_ransac_tensor_filter_full_size_pairs(backend):
         backend.set_ransac_scoring(backend.RANSAC_TENSOR_FILTER)
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
     assert int(res[0][0].min().item()) >> 32 > 1000
+
+
+def test_full_size_batch_equals_cpu_port(oracle, backend):
+    """BASELINE config 2 at full per-pair size (5 000 x 5 000 keypoints, 50 000 hypotheses, 20 refinement rounds): a batch of the bench
+    workload's pairs through the one-call back end equals the CPU port pose for pose, bit for bit (the check bench.py makes on 256 pairs)"""
+    c = S.CONFIGS[2]; P = 48; N = c["gen"]["num_kpts"]
+    b = S.make_pairs(P, first_pair=0, **c["gen"])
+    off = np.arange(P + 1, dtype=np.int32) * N
+    oracle.set_num_threads(os.cpu_count() or 1)
+    To, nm_o, ni_o = oracle.register_batched(b.src_des.reshape(-1, 32).numpy(), b.src_xyz.reshape(-1, 3).numpy(), off, b.tgt_des.reshape(-1, 32).numpy(),
+                                             b.tgt_xyz.reshape(-1, 3).numpy(), off, c["hypotheses"], 0, 0, c["dist_th"], c["similar_th"], c["refine_thr"], 20)
+    bd = b.to(DEV)
+    for scoring in (backend.RANSAC_TENSOR_FILTER, backend.RANSAC_FP32):
+        backend.set_ransac_scoring(scoring)
+        try:
+            T, nm, ni = backend.register_uniform(bd.src_des, bd.src_xyz, bd.tgt_des, bd.tgt_xyz, hypotheses=c["hypotheses"], dist_th=c["dist_th"],
+                                                 similar_th=c["similar_th"], refine_thr=c["refine_thr"], seed=0)
+        finally:
+            backend.set_ransac_scoring(backend.RANSAC_TENSOR_FILTER)
+        assert np.array_equal(nm.cpu().numpy(), nm_o) and np.array_equal(ni.cpu().numpy(), ni_o)
+        assert np.array_equal(T.cpu().numpy(), To)
+    recall, rte, rre = S.registration_recall(T.cpu(), b.T_gt)
+    assert recall == 1.0

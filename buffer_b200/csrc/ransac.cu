@@ -47,6 +47,7 @@ constexpr int RS_MAX_CTAS = 160;                   // upper bound of the persist
 
 // tensor-core scoring filter
 constexpr int RT_GROUPS = RS_WARPS / 4;         // warp groups of the epilogue: 4 warps = the 128 TMEM lanes (correspondences) of a tile
+constexpr int RT_EPI_WARPS = 4 * RT_GROUPS;     // epilogue warps (any further worker warps sit a flush out)
 constexpr int RT_HT = 20;                       // hypotheses per accumulator tile: 2 chunks of 32 TMEM columns = 5 hypothesis pairs x (x x' y y' z z') + 2 unused
 constexpr int RT_FLUSH = RT_GROUPS * RT_HT;     // hypotheses per flush = one 128 x 192 accumulator tile (a group reads its 64-column slice); two tiles ping-pong
 constexpr int RT_N = RT_GROUPS * 64;            // MMA N: small MMAs cost ~80 cycles each whatever their N (tools/microbench/mma_issue.cu), so one pair serves all groups
@@ -516,41 +517,43 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     int c0[10], c1[10];                                               // inlier counts of this thread's 2 x 10 hypotheses over its correspondences
 #pragma unroll
     for (int j = 0; j < 10; ++j) { c0[j] = 0; c1[j] = 0; }
-#ifdef RT_STAGGER
-    // The 12 warps are released by the same barrier and would run their phases (wait, tcgen05.ld, hand-back: latency; arithmetic: issue
-    // slots) in lock step; a one-time offset between the groups lets one group's arithmetic cover another's latencies.  The two-tile
-    // depth of the accumulator pipeline keeps the offset alive.
-    if (grp) { const long long t_ = clock64(); while (clock64() - t_ < (long long)(grp * RT_STAGGER)) { } }
-#endif
-    float va[32], vb[32];
-    for (int i = 0; i < ntiles; ++i) {
-        const uint32_t gi = tile0 + (uint32_t)i; const uint32_t buf = gi & 1u;
-        RTR(0, i);
-        mbar_wait(&sm.acc_full[buf], (gi >> 1) & 1u);
-        RTR(1, i);
+    auto acquire = [&](int i) {                                       // the accumulator of A tile i is complete
+        const uint32_t gi = tile0 + (uint32_t)i;
+        mbar_wait(&sm.acc_full[gi & 1u], (gi >> 1) & 1u);
         tc_fence_after();
         __syncwarp();
-        tmem_ld32_issue(taddr + buf * 256u, va); tmem_ld32_issue(taddr + buf * 256u + 32u, vb);
-        tmem_ld_wait(va); tmem_ld_pin(vb);
-        RTR(2, i);
+    };
+    auto release = [&](int i) {                                       // all TMEM reads of A tile i have landed: the buffer goes back to the tensor-core warp
         tc_fence_before();
         __syncwarp();
-        RTR(3, i);
-        if (lane == 0) mbar_arrive(&sm.acc_empty[buf]);              // the buffer goes back to the tensor-core warp
-        RTR(4, i);
-        process(va, c0, i, 0);
-        process(vb, c1, i, 1);
-        RTR(5, i);
+        if (lane == 0) mbar_arrive(&sm.acc_empty[(tile0 + (uint32_t)i) & 1u]);
+    };
+    auto col0 = [&](int i) { return taddr + ((tile0 + (uint32_t)i) & 1u) * 256u; };
+    if (warp < RT_EPI_WARPS) {
+        float va[32], vb[32];
+        for (int i = 0; i < ntiles; ++i) {
+            RTR(0, i);
+            acquire(i);
+            RTR(1, i);
+            tmem_ld32_issue(col0(i), va); tmem_ld32_issue(col0(i) + 32u, vb);
+            tmem_ld_wait(va); tmem_ld_pin(vb);
+            RTR(2, i);
+            release(i);
+            RTR(4, i);
+            process(va, c0, i, 0);
+            process(vb, c1, i, 1);
+            RTR(5, i);
+        }
+        // ---- totals over the 128 lanes x tiles ----
+#pragma unroll
+        for (int j = 0; j < RT_HT; ++j) {
+            const int tot = __reduce_add_sync(0xffffffffu, j < 10 ? c0[j % 10] : c1[j % 10]);
+            if (lane == j) atomicAdd(&sm.u.tc.cnt[hl0 + j], tot);
+        }
     }
 #ifdef RS_TIMING
     const long long tq2 = clock64();
 #endif
-    // ---- totals over the 128 lanes x tiles ----
-#pragma unroll
-    for (int j = 0; j < RT_HT; ++j) {
-        const int tot = __reduce_add_sync(0xffffffffu, j < 10 ? c0[j % 10] : c1[j % 10]);
-        if (lane == j) atomicAdd(&sm.u.tc.cnt[hl0 + j], tot);
-    }
     rs_sync();
 #ifdef RS_TRACE
     if (trace_on) for (int k = threadIdx.x; k < 16 * RTR_EV * RTR_TILES; k += RS_THREADS) g_trace[k] = (&sm.trace[0][0])[k];
@@ -773,7 +776,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
     if (tc_on) {
         if (threadIdx.x == 0) {
             for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 1); }
-            for (int t = 0; t < 2; ++t) { mbar_init(&sm.acc_full[t], 1); mbar_init(&sm.acc_empty[t], RS_WARPS); }     // every epilogue warp hands the buffer back
+            for (int t = 0; t < 2; ++t) { mbar_init(&sm.acc_full[t], 1); mbar_init(&sm.acc_empty[t], RT_EPI_WARPS); }     // every epilogue warp hands the buffer back
             mbar_fence_init();
             sm.tc_ntiles = 0;
         }

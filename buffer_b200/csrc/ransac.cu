@@ -35,7 +35,7 @@ namespace bfr {
 
 constexpr int RS_THREADS = 512;                 // worker threads: stage 1, fits, scoring / tensor-core epilogue
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_LAUNCH = RS_THREADS + 32;      // + the warp that feeds the tensor core (TMA of the A tiles, tcgen05.mma issue): 13 warps, <= 152 registers
+constexpr int RS_LAUNCH = RS_THREADS + 128;     // + four warps that feed the tensor core, one per epilogue warp group (20 warps: 96 registers, like 17 would be)
 constexpr int RS_CHUNK = 5120;                  // correspondences per shared-memory chunk; pairs with K <= RS_CHUNK stay resident
 #ifndef RS_S1_N
 #define RS_S1_N 4
@@ -62,7 +62,7 @@ constexpr float RT_PAD_Q = 32768.0f;            // target coordinate of the padd
 
 #ifdef RS_TRACE
 constexpr int RTR_EV = 8, RTR_TILES = 20;
-__device__ unsigned int g_trace[16 * RTR_EV * RTR_TILES];      // clocks of lane 0 of every warp of CTA 0 during one flush: [warp][tile][event]
+__device__ unsigned int g_trace[20 * RTR_EV * RTR_TILES];      // clocks of lane 0 of every warp of CTA 0 during one flush: [warp][tile][event]
 #define RTR(ev, tile) { if (trace_on && lane == 0 && (tile) < RTR_TILES) sm.trace[warp][(tile) * RTR_EV + (ev)] = (unsigned)clock64(); }
 #else
 #define RTR(ev, tile) { }
@@ -93,7 +93,7 @@ struct __align__(1024) RsSmem {
     } u;
     uint32_t q1[RS_Q1CAP];                      // queue 1: survivors of the cheap checks (hypothesis index); idle: partial counts / round results
     unsigned long long red[RS_WARPS];
-    uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_full[2], acc_empty[2];     // acc_*[accumulator buffer]
+    uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_full[RT_GROUPS][2], acc_empty[RT_GROUPS][2];     // acc_*[warp group][accumulator buffer]
     int tc_ntiles;                              // A tiles of the current item; < 0: the tensor-core warp leaves
     unsigned long long seq_best;                // confidence mode: state of the sequential replay
     uint32_t seq_bound;
@@ -102,7 +102,7 @@ struct __align__(1024) RsSmem {
     int qcount;
     uint32_t tmem_base;
 #ifdef RS_TRACE
-    unsigned int trace[16][8 * 20];
+    unsigned int trace[20][8 * 20];
 #endif
     uint32_t stat[4];                           // float bits: max |s|_1, max |q_i| of the pair, max |t_i| of the flush; [3] != 0: out of range / non-finite
 };
@@ -326,8 +326,8 @@ constexpr uint32_t RT_DESC_HI = 16u | (1u << 14);                    // SBO = 25
 BFR_DEVINL uint32_t rt_desc_lo(const void* smem) { return ((smem_u32(smem) >> 4) & 0x3FFFu) | (8u << 16); }     // LBO = 128 B (K direction)
 BFR_DEVINL void rt_issue_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t b1_lo, uint32_t b2_lo, uint32_t bar_acc_full, uint32_t bar_a_empty)
 {
-    // instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 192, M = 128
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(RT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // instruction descriptor (kind::f16): D = F32, A = B = F16, both K-major, N = 64, M = 128
+    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     asm volatile("{\n\t.reg .b64 da, db1, db2;\n\t.reg .pred pt, pf;\n\t"
                  "mov.b64 da, {%1, %4};\n\tmov.b64 db1, {%2, %4};\n\tmov.b64 db2, {%3, %4};\n\t"
                  "setp.eq.u32 pt, %0, %0;\n\tsetp.ne.u32 pf, %0, %0;\n\t"
@@ -345,12 +345,13 @@ BFR_DEVINL bool mbar_test(uint32_t bar, uint32_t parity)
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0u;
 }
-BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scratch)
+BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scratch, int grp)
 {
     const int lane = threadIdx.x & 31;
-    const uint32_t tmem_base = sm.tmem_base;
-    const uint32_t a_lo0 = rt_desc_lo(sm.u.tc.a_ring[0]), b1_lo = rt_desc_lo(sm.u.tc.b_op[0]), b2_lo = rt_desc_lo(sm.u.tc.b_op[1]);
-    const uint32_t bar_af = smem_u32(&sm.a_full[0]), bar_ae = smem_u32(&sm.a_empty[0]), bar_cf = smem_u32(&sm.acc_full[0]);
+    const uint32_t tmem_grp = sm.tmem_base + (uint32_t)(grp * 128);
+    const uint32_t a_lo0 = rt_desc_lo(sm.u.tc.a_ring[0]);
+    const uint32_t b1_lo = rt_desc_lo(sm.u.tc.b_op[0]) + (uint32_t)(grp * (64 * 32 >> 4)), b2_lo = rt_desc_lo(sm.u.tc.b_op[1]) + (uint32_t)(grp * (64 * 32 >> 4));
+    const uint32_t bar_af = smem_u32(&sm.a_full[0]), bar_ae = smem_u32(&sm.a_empty[0]), bar_cf = smem_u32(&sm.acc_full[grp][0]);
     const uint32_t ring = smem_u32(sm.u.tc.a_ring[0]);
     uint32_t g0 = 0;                                                  // A tiles consumed before this flush
     for (;;) {
@@ -358,20 +359,34 @@ BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scrat
         const int ntiles = *reinterpret_cast<volatile int*>(&sm.tc_ntiles);
         if (ntiles < 0) break;
         if (lane == 0) {
-            auto load = [&](int j) {                                  // A tile j -> its ring stage, once the MMAs on the previous occupant have completed
+            // The A-tile copies are dealt out over the four warps (tile j by warp j % 4), RT_AHEAD tiles ahead of the issue: the copy of tile
+            // i + RT_AHEAD goes into the stage of tile i + RT_AHEAD - 8 and waits until every group's MMAs on that tile have completed, so the
+            // groups may drift 8 - RT_AHEAD tiles apart before a fast group's warp blocks (the slowest group's warp never does: no deadlock).
+            auto load = [&](int j) {
                 const uint32_t gj = g0 + (uint32_t)j, st = gj & (RT_STAGES - 1);
                 mbar_wait(&sm.a_empty[st], ((gj / RT_STAGES) & 1u) ^ 1u);
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_af + st * 8u), "r"((uint32_t)RT_TILE_BYTES) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(ring + st * RT_TILE_BYTES), "l"(scratch + (size_t)j * RT_TILE_BYTES), "r"((uint32_t)RT_TILE_BYTES), "r"(bar_af + st * 8u) : "memory");
             };
-            for (int j = 0; j < RT_STAGES - 1 && j < ntiles; ++j) load(j);
+            constexpr int RT_AHEAD = 4;
+            if (grp < ntiles) load(grp);                              // tiles 0 .. 3
+            if (ntiles > 0) mbar_wait(&sm.a_full[g0 & (RT_STAGES - 1)], (g0 / RT_STAGES) & 1u);
             for (int i = 0; i < ntiles; ++i) {
                 const uint32_t gi = g0 + (uint32_t)i, st = gi & (RT_STAGES - 1), buf = gi & 1u;
-                mbar_wait(&sm.acc_empty[buf], ((gi >> 1) & 1u) ^ 1u);                 // every epilogue warp has pulled the buffer's previous tile out of TMEM
-                mbar_wait(&sm.a_full[st], (gi / RT_STAGES) & 1u);
-                rt_issue_tile(tmem_base + buf * 256u, a_lo0 + st * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_cf + buf * 8u, bar_ae + st * 8u);
-                if (i + RT_STAGES - 1 < ntiles) load(i + RT_STAGES - 1);             // into the stage of tile i - 1
+#ifdef RS_TRACE
+                const bool trace_on = blockIdx.x == 0 && g0 >= 80u && g0 < 120u; const int warp = threadIdx.x >> 5;
+#endif
+                RTR(0, i);
+                mbar_wait(&sm.acc_empty[grp][buf], ((gi >> 1) & 1u) ^ 1u);            // the group's four warps have pulled the buffer's previous tile out of TMEM
+                RTR(1, i);
+                RTR(2, i);
+                rt_issue_tile(tmem_grp + buf * 64u, a_lo0 + st * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_cf + buf * 8u, bar_ae + st * 8u);
+                RTR(3, i);
+                // behind the issue, while the group is busy with the other buffer: this warp's copy, and the A tile of the next issue
+                const int j = i + RT_AHEAD;
+                if (j < ntiles && (j & (RT_GROUPS - 1)) == grp) load(j);
+                if (i + 1 < ntiles) mbar_wait(&sm.a_full[(gi + 1u) & (RT_STAGES - 1)], ((gi + 1u) / RT_STAGES) & 1u);
             }
         }
         g0 += (uint32_t)ntiles;
@@ -483,7 +498,7 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     rs_sync_all();                              // the tensor-core warp starts on this flush
     const int grp = warp >> 2, qd = warp & 3;
     const int ntiles = (K + RT_TILE - 1) / RT_TILE;
-    const uint32_t taddr = sm.tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 64);
+    const uint32_t taddr = sm.tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 128);
     const f32x2 negT = pack2(-d2max, -d2max);
     const int hl0 = grp * RT_HT;                                      // flush-local index of this thread's first hypothesis
     // one 32-column chunk: 5 hypothesis pairs; sign bit of d2~ - d2max -> count, |.| -> band test
@@ -519,16 +534,16 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     for (int j = 0; j < 10; ++j) { c0[j] = 0; c1[j] = 0; }
     auto acquire = [&](int i) {                                       // the accumulator of A tile i is complete
         const uint32_t gi = tile0 + (uint32_t)i;
-        mbar_wait(&sm.acc_full[gi & 1u], (gi >> 1) & 1u);
+        mbar_wait(&sm.acc_full[grp][gi & 1u], (gi >> 1) & 1u);
         tc_fence_after();
         __syncwarp();
     };
     auto release = [&](int i) {                                       // all TMEM reads of A tile i have landed: the buffer goes back to the tensor-core warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.acc_empty[(tile0 + (uint32_t)i) & 1u]);
+        if (lane == 0) mbar_arrive(&sm.acc_empty[grp][(tile0 + (uint32_t)i) & 1u]);
     };
-    auto col0 = [&](int i) { return taddr + ((tile0 + (uint32_t)i) & 1u) * 256u; };
+    auto col0 = [&](int i) { return taddr + ((tile0 + (uint32_t)i) & 1u) * 64u; };
     if (warp < RT_EPI_WARPS) {
         float va[32], vb[32];
         for (int i = 0; i < ntiles; ++i) {
@@ -556,8 +571,8 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
 #endif
     rs_sync();
 #ifdef RS_TRACE
-    if (trace_on) for (int k = threadIdx.x; k < 16 * RTR_EV * RTR_TILES; k += RS_THREADS) g_trace[k] = (&sm.trace[0][0])[k];
-    else if (blockIdx.x == 0 && tile0 < 40u) for (int k = threadIdx.x; k < 16 * RTR_EV * RTR_TILES; k += RS_THREADS) (&sm.trace[0][0])[k] = 0u;
+    if (trace_on) for (int k = threadIdx.x; k < 20 * RTR_EV * RTR_TILES; k += RS_THREADS) g_trace[k] = (&sm.trace[0][0])[k];
+    else if (blockIdx.x == 0 && tile0 < 40u) for (int k = threadIdx.x; k < 20 * RTR_EV * RTR_TILES; k += RS_THREADS) (&sm.trace[0][0])[k] = 0u;
 #endif
     const int r = (int)threadIdx.x < n ? sm.u.tc.cnt[threadIdx.x] : 0;
     if (threadIdx.x == 0) { sm.stat[2] = 0u; sm.stat[3] = 0u; }
@@ -775,12 +790,13 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
 
     if (tc_on) {
         if (threadIdx.x == 0) {
-            for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], 1); }
-            for (int t = 0; t < 2; ++t) { mbar_init(&sm.acc_full[t], 1); mbar_init(&sm.acc_empty[t], RT_EPI_WARPS); }     // every epilogue warp hands the buffer back
+            for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], RT_GROUPS); }   // a stage is free once every group's MMAs have read it
+            for (int t = 0; t < 2 * RT_GROUPS; ++t) { mbar_init(&sm.acc_full[t >> 1][t & 1], 1); mbar_init(&sm.acc_empty[t >> 1][t & 1], 4); }
             mbar_fence_init();
             sm.tc_ntiles = 0;
         }
         if (warp == RS_WARPS) tmem_alloc512(&sm.tmem_base);
+        static_assert(RT_GROUPS == 4 && RS_LAUNCH == RS_THREADS + 32 * RT_GROUPS, "one tensor-core warp per epilogue warp group");
         for (int i = threadIdx.x; i < (int)sizeof(sm.u.tc.b_op) / 16; i += RS_LAUNCH) reinterpret_cast<uint4*>(sm.u.tc.b_op)[i] = make_uint4(0u, 0u, 0u, 0u);
         if (threadIdx.x < 4) sm.stat[threadIdx.x] = 0u;
         fence_proxy_async();
@@ -788,12 +804,12 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         __syncthreads();
         tc_fence_after();
     }
-    if (warp == RS_WARPS) {                                           // the tensor-core warp
+    if (warp >= RS_WARPS) {                                           // the tensor-core warps
         if (tc_on) {
-            tc_warp_loop(sm, tc_scratch + (size_t)blockIdx.x * RT_MAX_TILES * RT_TILE_BYTES);
+            tc_warp_loop(sm, tc_scratch + (size_t)blockIdx.x * RT_MAX_TILES * RT_TILE_BYTES, warp - RS_WARPS);
             tc_fence_before();
-            __syncwarp();
-            tmem_dealloc512(sm.tmem_base);
+            asm volatile("bar.sync 3, 128;" ::: "memory");            // every tensor-core warp is done with tensor memory
+            if (warp == RS_WARPS) tmem_dealloc512(sm.tmem_base);
         }
         return;
     }
@@ -1117,7 +1133,7 @@ lrf_vote_select_kernel(const float4* __restrict__ corr, const int32_t* __restric
 
 #ifdef RS_TRACE
 }
-extern "C" __attribute__((visibility("default"))) unsigned bfr_dbg_ransac_trace(unsigned* out) { cudaMemcpyFromSymbol(out, bfr::g_trace, sizeof(unsigned) * 16 * 8 * 20); return 16 * 8 * 20; }
+extern "C" __attribute__((visibility("default"))) unsigned bfr_dbg_ransac_trace(unsigned* out) { cudaMemcpyFromSymbol(out, bfr::g_trace, sizeof(unsigned) * 20 * 8 * 20); return 20 * 8 * 20; }
 namespace bfr {
 #endif
 #ifdef RS_TIMING

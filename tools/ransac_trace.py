@@ -15,20 +15,22 @@ b = S.make_pairs(P, first_pair=0, device=dev, **c["gen"])
 off = (torch.arange(P + 1, dtype=torch.int32) * N).to(dev)
 rm = B.mutual_matching_batched(b.src_des.reshape(P * N, 32), b.tgt_des.reshape(P * N, 32), off, off, N, N, b.src_xyz.reshape(P * N, 3), b.tgt_xyz.reshape(P * N, 3), want_nn=False, want_mids=False)
 B.ransac_batched(rm["corr"], off, rm["n_mutual"], c["hypotheses"], c["dist_th"], c["similar_th"], splits=1); torch.cuda.synchronize()
-L = ctypes.CDLL(_lib.SO_PATH); out = np.zeros(16 * 8 * NT, dtype=np.uint32)
+L = ctypes.CDLL(_lib.SO_PATH); out = np.zeros(20 * 8 * NT, dtype=np.uint32)
 L.bfr_dbg_ransac_trace.restype = ctypes.c_uint
-L.bfr_dbg_ransac_trace(ctypes.c_void_p(out.ctypes.data)); ev = out.reshape(16, NT, 8).astype(np.int64)
+L.bfr_dbg_ransac_trace(ctypes.c_void_p(out.ctypes.data)); ev = out.reshape(20, NT, 8).astype(np.int64); iss = ev[16:]; ev = ev[:16]
 t0 = ev[:, 0, 0].min()
 rel = lambda x: int((x - t0) & 0xffffffff)
 for w in (0, 1, 4, 7, 8, 9, 15):
     line = []
     for i in range(8, 14):
         e = ev[w, i]
-        line.append("%d: W%d F%d L%d P%d H%d%s M%d%s" % (i, rel(e[0]), rel(e[1]), rel(e[2]), rel(e[3]), rel(e[4]), "*" if e[7] else "", rel(e[5]), (" T%d" % rel(e[6])) if e[6] else ""))
+        line.append("%d: W%d F%d L%d H%d M%d" % (i, rel(e[0]), rel(e[1]), rel(e[2]), rel(e[4]), rel(e[5])))
     print("warp %2d | " % w + " | ".join(line))
+for g in range(4):
+    print("issuer %d | " % g + " | ".join("%d: wait-empty %d, seen %d, A tile %d, issued %d" % (i, rel(iss[g, i, 0]), rel(iss[g, i, 1]), rel(iss[g, i, 2]), rel(iss[g, i, 3])) for i in range(8, 12)))
+print("issuer means: buffer wait %.0f, A-tile wait %.0f, issue %.0f; hand-back of the group's last warp -> issued %.0f; issued -> first warp sees the tile %.0f" % (
+    float(np.mean((iss[:, 2:, 1] - iss[:, 2:, 0]) & 0xffffffff)), float(np.mean((iss[:, 2:, 2] - iss[:, 2:, 1]) & 0xffffffff)), float(np.mean((iss[:, 2:, 3] - iss[:, 2:, 2]) & 0xffffffff)),
+    float(np.mean([((iss[g, 4:, 3] - ev[4 * g:4 * g + 4, 2:-2, 4].max(0)) & 0xffffffff).mean() for g in range(4)])),
+    float(np.mean([((ev[4 * g:4 * g + 4, 4:, 1].min(0) - iss[g, 4:, 3]) & 0xffffffff).mean() for g in range(4)]))))
 d = lambda a, b: float(np.mean((ev[:, 2:, a] - ev[:, 2:, b]) & 0xffffffff))
-print("means over warps and tiles: wait %.0f, ld %.0f, prepare %.0f, hand back %.0f, math %.0f, tile period %.0f" % (d(1, 0), d(2, 1), d(3, 2), d(4, 3), d(5, 4), float(np.mean((ev[:, 3:, 0] - ev[:, 2:-1, 0]) & 0xffffffff))))
-last = (ev[:, :, 7] != 0)
-print("last arriver counts per warp:", last.sum(1).tolist())
-print("hand back incl. MMA issue when last: %.0f" % float(np.mean(((ev[:, :, 4] - ev[:, :, 3]) & 0xffffffff)[last])))
-print("feeder prepare (incl. A-tile wait): %.0f; others: %.0f" % (float(np.mean((ev[[0, 8], 2:, 3] - ev[[0, 8], 2:, 2]) & 0xffffffff)), float(np.mean((ev[[1, 2, 3, 9, 10], 2:, 3] - ev[[1, 2, 3, 9, 10], 2:, 2]) & 0xffffffff))))
+print("means over warps and tiles: wait %.0f, ld %.0f, hand back %.0f, math %.0f, tile period %.0f" % (d(1, 0), d(2, 1), d(4, 2), d(5, 4), float(np.mean((ev[:, 3:, 0] - ev[:, 2:-1, 0]) & 0xffffffff))))

@@ -223,9 +223,14 @@ def ransac_finalize_batched(corr, corr_off, corr_cnt, best_packed, dist_th, simi
     return T, inl, bh
 
 
-def _default_splits(P):
-    """work items per pair of the persistent RANSAC kernel (one 512-thread CTA per SM): enough items to balance 148 SMs"""
-    return max(1, min(64, (4 * 148 + P - 1) // max(P, 1)))
+def _default_splits(P, sms=None):
+    """work items per pair of the persistent RANSAC kernel (one CTA per SM): the split count s in 1..64 that minimises
+    ceil(P s / SMs) (1 / s + 0.06) - rounds of items times the work of an item, 0.06 of a pair's work being what an item costs up front
+    (loading the correspondences, building the operand tiles).  1 623 pairs -> 1 (10.97 rounds), 203 pairs (one of 8 ranks) -> 2, one pair -> 64."""
+    if sms is None:
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count if torch.cuda.is_available() else 148
+    P = max(int(P), 1)
+    return min(range(1, 65), key=lambda s: (math.ceil(P * s / sms) * (1.0 / s + 0.06), s))
 
 
 class RansacResult:

@@ -5,7 +5,7 @@
 // scoring block (models/BUFFER.py:303-311).  Semantics and exact arithmetic: oracle/bfr_oracle.c (orc_hypothesis,
 // orc_count_inliers, orc_ransac, orc_score_hypotheses, orc_lrf_vote); DESIGN.md §K2/§K3.
 //
-// ransac_kernel: persistent CTAs (512 threads, one per SM) walk work items = (pair, slice of the
+// ransac_kernel: persistent CTAs (512 worker threads + four tensor-core warps, one CTA per SM) walk work items = (pair, slice of the
 // hypothesis range) round-robin.  A pair's correspondences (up to RS_CHUNK = 5120, 24 bytes each: 120 KB) are loaded ONCE per item into
 // shared memory in a pair-interleaved layout and serve the random sample gathers of stage 1, the fits and the exact scoring loop; larger
 // pairs stream through the same buffer in chunks and gather their samples from global memory.  Per round every thread draws RS_S1
@@ -17,8 +17,8 @@
 //    LDS.128 broadcasts; ~11 instructions per (hypothesis, correspondence).
 //  * tensor-core filter (tc_flush, the default for shared-memory-resident pairs when the caller passes scratch memory): the residual
 //    components x_i(h,c) = sum_j R_ij s_j + t_i - q_i are bilinear in (R_i, t_i | 1) and (s, 1, q), so a 128-correspondence x
-//    80-hypothesis block of all three components is ONE 128 x 256 accumulator tile of two K = 16 tcgen05.mma kind::f16 on 2-level f16
-//    splits of the FP32 operands (relative operand error 2^-24).  The epilogue (thread = correspondence, TMEM -> registers) needs three
+//    20-hypothesis block of all three components is ONE 128 x 64 accumulator tile of two K = 16 tcgen05.mma kind::f16 on 2-level f16
+//    splits of the FP32 operands (relative operand error 2^-24); four warp groups run four such pipelines side by side.  The epilogue (thread = correspondence, TMEM -> registers) needs three
 //    FMAs, a sign-bit add and a band test per (h,c); only pairs whose approximate d^2 lies within a rigorous error band of the threshold
 //    (none to a handful per pair) are re-evaluated with the oracle's FP32 chain, so the counts stay bit-exact.
 // The inlier count never leaves the CTA; a CTA's best (count << 32 | ~h) goes out with one 64-bit atomicMax per item.
@@ -49,8 +49,8 @@ constexpr int RS_MAX_CTAS = 160;                   // upper bound of the persist
 constexpr int RT_GROUPS = RS_WARPS / 4;         // warp groups of the epilogue: 4 warps = the 128 TMEM lanes (correspondences) of a tile
 constexpr int RT_EPI_WARPS = 4 * RT_GROUPS;     // epilogue warps (any further worker warps sit a flush out)
 constexpr int RT_HT = 20;                       // hypotheses per accumulator tile: 2 chunks of 32 TMEM columns = 5 hypothesis pairs x (x x' y y' z z') + 2 unused
-constexpr int RT_FLUSH = RT_GROUPS * RT_HT;     // hypotheses per flush = one 128 x 192 accumulator tile (a group reads its 64-column slice); two tiles ping-pong
-constexpr int RT_N = RT_GROUPS * 64;            // MMA N: small MMAs cost ~80 cycles each whatever their N (tools/microbench/mma_issue.cu), so one pair serves all groups
+constexpr int RT_FLUSH = RT_GROUPS * RT_HT;     // hypotheses per flush: every group ping-pongs between two 128 x 64 accumulator tiles (4 x 2 x 64 = 512 TMEM columns)
+constexpr int RT_N = RT_GROUPS * 64;            // B rows of a flush (a group's MMAs read its 64-row slice)
 constexpr int RT_QCAP = RT_FLUSH + RS_THREADS;  // queue 2 (tensor-core scoring): < RT_FLUSH leftovers plus the survivors of one fit block
 constexpr int RT_TILE = 128;                    // correspondences per A tile (MMA M)
 constexpr int RT_TILE_BYTES = RT_TILE * 32;     // K = 16 f16 per row
@@ -85,7 +85,7 @@ struct __align__(1024) RsSmem {
         } ex;
         struct {                                // tensor-core scoring
             unsigned char a_ring[RT_STAGES][RT_TILE_BYTES];   // A tiles: 128 correspondences x 16 f16, unswizzled K-major core matrices
-            unsigned char b_op[2][RT_N * 32];                 // [B1 | B2]: 192 (hypothesis, component) rows x 16 f16
+            unsigned char b_op[2][RT_N * 32];                 // [B1 | B2]: 256 (hypothesis, component) rows x 16 f16, group g = rows 64 g ..
             float q[12][RT_QCAP];
             uint32_t qh[RT_QCAP];
             int cnt[RT_FLUSH];                                // inlier counts of the hypotheses of the current flush
@@ -94,7 +94,7 @@ struct __align__(1024) RsSmem {
     uint32_t q1[RS_Q1CAP];                      // queue 1: survivors of the cheap checks (hypothesis index); idle: partial counts / round results
     unsigned long long red[RS_WARPS];
     uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_full[RT_GROUPS][2], acc_empty[RT_GROUPS][2];     // acc_*[warp group][accumulator buffer]
-    int tc_ntiles;                              // A tiles of the current item; < 0: the tensor-core warp leaves
+    int tc_ntiles;                              // A tiles of the current item; < 0: the tensor-core warps leave
     unsigned long long seq_best;                // confidence mode: state of the sequential replay
     uint32_t seq_bound;
     int seq_stop;
@@ -123,7 +123,7 @@ struct __align__(16) ScSmem {
 extern __shared__ __align__(1024) unsigned char rs_smem_raw[];
 BFR_DEVINL RsSmem& rs_smem() { return *reinterpret_cast<RsSmem*>(rs_smem_raw); }
 
-// barrier of the worker threads (the tensor-core warp is not part of it) / of all threads (hands a flush to the tensor-core warp)
+// barrier of the worker threads (the tensor-core warps are not part of it) / of all threads (hands a flush to the tensor-core warps)
 BFR_DEVINL void rs_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RS_THREADS) : "memory"); }
 BFR_DEVINL void rs_sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(RS_LAUNCH) : "memory"); }
 
@@ -277,7 +277,7 @@ BFR_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: 
 BFR_DEVINL float min3abs(float a, float b, float c) { float d; asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(fabsf(b)), "f"(fabsf(c))); return d; }
 
 // Once per item: the pair's A tiles (f16 splits of every resident correspondence, padded to whole tiles) go to this CTA's scratch in
-// global memory (it stays in L2; the tensor-core warp streams it back tile by tile with 1-D TMA copies, once per flush), and the
+// global memory (it stays in L2; the tensor-core warps stream it back tile by tile with 1-D TMA copies, once per flush), and the
 // pair's magnitude bounds are reduced.  Returns false if the pair must be scored exactly (coordinates out of range / non-finite).
 BFR_DEVINL bool tc_prepare_pair(RsSmem& sm, int K, unsigned char* __restrict__ scratch, float& s1max, float& qmax)
 {
@@ -421,13 +421,13 @@ __device__ __noinline__ uint32_t tc_recheck(uint32_t c, int qbase, int nvalid, f
     return fix;
 }
 
-// Score the queued hypotheses [base, base + n), n <= RT_FLUSH, on the tensor cores.  The flush's 60 hypotheses x 3 components are the 192
-// columns of an accumulator tile; warp group g (warps 4g .. 4g + 3) reads columns 64 g .. 64 g + 63 = flush-local hypotheses 20g .. 20g + 19
-// (2 chunks of 32 columns; a chunk holds 10 hypotheses as 5 pairs (x_a x_b y_a y_b z_a z_b) so that one FFMA2 squares a component of two
-// hypotheses).  Two tiles ping-pong: while the threads work on the tile of A tile i (thread = correspondence: warp w reads TMEM lanes
-// 32 (w % 4) ..), the tensor core fills the other buffer with A tile i + 1.  A warp pulls its 64 columns into registers, hands the buffer
-// back to the tensor-core warp (which issues A tile i + 2 once all 12 warps have), and only then does the arithmetic.
-// `tile0` = A tiles consumed before this flush (the mbarrier phase clock).
+// Score the queued hypotheses [base, base + n), n <= RT_FLUSH, on the tensor cores.  Warp group g (warps 4g .. 4g + 3 = the 128 TMEM lanes
+// of a tile; thread = correspondence) owns flush-local hypotheses 20g .. 20g + 19: their 3 components are the 64 columns of the group's
+// accumulator tiles (2 chunks of 32 columns; a chunk holds 10 hypotheses as 5 pairs (x_a x_b y_a y_b z_a z_b) so that one FFMA2 squares a
+// component of two hypotheses).  Every group has its own pipeline: two ping-pong buffers, its own barriers and its own tensor-core warp.
+// While the group works on the tile of A tile i, the tensor core fills the other buffer with A tile i + 1.  A warp pulls its 64 columns
+// into registers, hands the buffer back (the group's tensor-core warp issues A tile i + 2 once all four warps have), and only then does
+// the arithmetic.  `tile0` = A tiles consumed before this flush (the mbarrier phase clock).
 // Returns, in threads < n, the exact inlier count of hypothesis base + threadIdx.x; bit 30 is set (in every thread) if the tensor-core path
 // ran, i.e. ceil(K / 128) A tiles were consumed.  Out of line: ransac_item flushes from three places.
 __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float s1max, float qmax, uint32_t tile0)
@@ -495,7 +495,7 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     const long long tq1 = clock64();
 #endif
     // ---- epilogue: thread = correspondence ----
-    rs_sync_all();                              // the tensor-core warp starts on this flush
+    rs_sync_all();                              // the tensor-core warps start on this flush
     const int grp = warp >> 2, qd = warp & 3;
     const int ntiles = (K + RT_TILE - 1) / RT_TILE;
     const uint32_t taddr = sm.tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 128);
@@ -538,7 +538,7 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
         tc_fence_after();
         __syncwarp();
     };
-    auto release = [&](int i) {                                       // all TMEM reads of A tile i have landed: the buffer goes back to the tensor-core warp
+    auto release = [&](int i) {                                       // all TMEM reads of A tile i have landed: the buffer goes back to the group's tensor-core warp
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.acc_empty[grp][(tile0 + (uint32_t)i) & 1u]);
@@ -784,7 +784,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
     if ((smem_u32(&sm) & 127u) != 0u) __trap();                       // round-up of the pointer: it would turn every access into a generic load)
     const float d2max = __fmul_rn(dist_th, dist_th), sim2 = __fmul_rn(similar_th, similar_th);
     const bool conf = confidence > 0.0f && confidence < 1.0f;
-    const bool tc_on = tc_scratch != nullptr && !conf;                // kernel-uniform: the tensor-core warp serves this launch
+    const bool tc_on = tc_scratch != nullptr && !conf;                // kernel-uniform: the tensor-core warps serve this launch
     const uint32_t nh = h_end - h_begin;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -862,7 +862,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
             if (b) atomicMax(best_packed + p, b);
         }
     }
-    if (tc_on) {                                                      // release the tensor-core warp
+    if (tc_on) {                                                      // release the tensor-core warps
         rs_sync();
         if (threadIdx.x == 0) sm.tc_ntiles = -1;
         rs_sync_all();

@@ -69,8 +69,7 @@ __device__ unsigned int g_trace[20 * RTR_EV * RTR_TILES];      // clocks of lane
 #endif
 #ifdef RS_TIMING
 __device__ unsigned long long g_rs_dbg[8];
-__device__ unsigned long long g_rt_dbg2[8];     // issue path: a_empty wait + TMA issue, a_full wait + MMA issue, issues; thread 0: pure tcgen05.ld, hand-back
-__device__ unsigned long long g_rt_dbg[8];      // tc_flush, summed over thread 0 of every CTA: build, wait acc_full, tcgen05.ld, math + issue, reduce, flushes, tiles
+__device__ unsigned long long g_rt_dbg[8];      // tc_flush, summed over thread 0 of every CTA: [0] B operands + bounds, [1] the tile loop, [4] count reduction, [5] flushes, [6] A tiles
 #define RST(acc, stmt) { const long long t_ = clock64(); stmt; acc += clock64() - t_; }
 #else
 #define RST(acc, stmt) { stmt; }
@@ -93,7 +92,8 @@ struct __align__(1024) RsSmem {
     } u;
     uint32_t q1[RS_Q1CAP];                      // queue 1: survivors of the cheap checks (hypothesis index); idle: partial counts / round results
     unsigned long long red[RS_WARPS];
-    uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_full[RT_GROUPS][2], acc_empty[RT_GROUPS][2];     // acc_*[warp group][accumulator buffer]
+    uint64_t a_full[RT_STAGES], a_empty[RT_STAGES], acc_empty[RT_GROUPS][2], acc_full[RT_GROUPS][2];     // acc_*[warp group][accumulator buffer]
+    uint64_t flush_go;                          // one arrival per flush (or at the end of the kernel): the tensor-core warps may read tc_ntiles and the B operands
     int tc_ntiles;                              // A tiles of the current item; < 0: the tensor-core warps leave
     unsigned long long seq_best;                // confidence mode: state of the sequential replay
     uint32_t seq_bound;
@@ -123,9 +123,8 @@ struct __align__(16) ScSmem {
 extern __shared__ __align__(1024) unsigned char rs_smem_raw[];
 BFR_DEVINL RsSmem& rs_smem() { return *reinterpret_cast<RsSmem*>(rs_smem_raw); }
 
-// barrier of the worker threads (the tensor-core warps are not part of it) / of all threads (hands a flush to the tensor-core warps)
+// barrier of the worker threads (the tensor-core warps are not part of it; a flush is handed to them through the flush_go mbarrier)
 BFR_DEVINL void rs_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RS_THREADS) : "memory"); }
-BFR_DEVINL void rs_sync_all() { asm volatile("bar.sync 2, %0;" ::"n"(RS_LAUNCH) : "memory"); }
 
 // cooperative load of correspondences [c0, c0 + CHUNK) of one pair (8-float records) into the pair-interleaved layout
 template <int NF, int CHUNK, int THREADS>
@@ -263,10 +262,6 @@ BFR_DEVINL unsigned long long pack_count(int count, uint32_t h) { return ((unsig
 // A B1^T + A B2^T = x_i(h,c) up to |error| <= 3 * 2^-24 * B' from the splits (B' = sum_j |R_ij s_j| + |t_i| + |q_i|) plus the
 // accumulation error of the tensor core (measured: total 2^-21.6 B', tools/microbench/rs_mma.cu; budgeted here: 2^-19 B').
 BFR_DEVINL uint32_t rt_row_offset(int r) { return (uint32_t)((r >> 3) * 256 + (r & 7) * 16); }     // first 16-byte half; the second is + 128
-BFR_DEVINL uint64_t rt_desc(const void* smem)
-{   // LBO = 128 B (K direction), SBO = 256 B (row groups), descriptor version 1, no swizzle
-    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFFu) | (8ull << 16) | (16ull << 32) | (1ull << 46);
-}
 BFR_DEVINL void split_f16(float v, __half& hi, __half& lo)
 {
     hi = __float2half_rn(v);
@@ -339,12 +334,6 @@ BFR_DEVINL void rt_issue_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t b1_lo, ui
                  ::"r"(tmem_d), "r"(a_lo), "r"(b1_lo), "r"(b2_lo), "r"(RT_DESC_HI), "r"(idesc), "r"(bar_acc_full), "r"(bar_a_empty) : "memory");
 }
 static_assert(RT_STAGES == 8, "the ring index is taken with a mask");
-BFR_DEVINL bool mbar_test(uint32_t bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0u;
-}
 BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scratch, int grp)
 {
     const int lane = threadIdx.x & 31;
@@ -354,8 +343,8 @@ BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scrat
     const uint32_t bar_af = smem_u32(&sm.a_full[0]), bar_ae = smem_u32(&sm.a_empty[0]), bar_cf = smem_u32(&sm.acc_full[grp][0]);
     const uint32_t ring = smem_u32(sm.u.tc.a_ring[0]);
     uint32_t g0 = 0;                                                  // A tiles consumed before this flush
-    for (;;) {
-        rs_sync_all();
+    for (uint32_t flush = 0;; ++flush) {
+        mbar_wait(&sm.flush_go, flush & 1u);
         const int ntiles = *reinterpret_cast<volatile int*>(&sm.tc_ntiles);
         if (ntiles < 0) break;
         if (lane == 0) {
@@ -364,7 +353,7 @@ BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scrat
             // groups may drift 8 - RT_AHEAD tiles apart before a fast group's warp blocks (the slowest group's warp never does: no deadlock).
             auto load = [&](int j) {
                 const uint32_t gj = g0 + (uint32_t)j, st = gj & (RT_STAGES - 1);
-                mbar_wait(&sm.a_empty[st], ((gj / RT_STAGES) & 1u) ^ 1u);
+                if (gj >= (uint32_t)RT_STAGES) mbar_wait(&sm.a_empty[st], ((gj / RT_STAGES) & 1u) ^ 1u);     // (the first occupant of a stage waits for nobody)
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_af + st * 8u), "r"((uint32_t)RT_TILE_BYTES) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(ring + st * RT_TILE_BYTES), "l"(scratch + (size_t)j * RT_TILE_BYTES), "r"((uint32_t)RT_TILE_BYTES), "r"(bar_af + st * 8u) : "memory");
@@ -378,7 +367,7 @@ BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scrat
                 const bool trace_on = blockIdx.x == 0 && g0 >= 80u && g0 < 120u; const int warp = threadIdx.x >> 5;
 #endif
                 RTR(0, i);
-                mbar_wait(&sm.acc_empty[grp][buf], ((gi >> 1) & 1u) ^ 1u);            // the group's four warps have pulled the buffer's previous tile out of TMEM
+                if (gi >= 2u) mbar_wait(&sm.acc_empty[grp][buf], ((gi >> 1) & 1u) ^ 1u);   // the group's four warps have pulled the buffer's previous tile out of TMEM
                 RTR(1, i);
                 RTR(2, i);
                 rt_issue_tile(tmem_grp + buf * 64u, a_lo0 + st * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_cf + buf * 8u, bar_ae + st * 8u);
@@ -438,7 +427,7 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     const bool trace_on = blockIdx.x == 0 && tile0 >= 80u && tile0 < 120u;
 #endif
 #ifdef RS_TIMING
-    long long tq0 = clock64(), tq_wait = 0, tq_ld = 0, tq_math = 0, tq_x[3] = { 0, 0, 0 };
+    const long long tq0 = clock64();
 #endif
     // ---- B operands of the flush + the largest |t_i| ----
     if (threadIdx.x < RT_FLUSH) sm.u.tc.cnt[threadIdx.x] = 0;
@@ -495,7 +484,7 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     const long long tq1 = clock64();
 #endif
     // ---- epilogue: thread = correspondence ----
-    rs_sync_all();                              // the tensor-core warps start on this flush
+    if (threadIdx.x == 0) mbar_arrive(&sm.flush_go);    // the tensor-core warps start on this flush (every worker is past the rs_sync above)
     const int grp = warp >> 2, qd = warp & 3;
     const int ntiles = (K + RT_TILE - 1) / RT_TILE;
     const uint32_t taddr = sm.tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(grp * 128);
@@ -579,10 +568,8 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     rs_sync();
 #ifdef RS_TIMING
     if (threadIdx.x == 0) {
-        atomicAdd(&g_rt_dbg[7], (unsigned long long)tq_x[2]);
-        atomicAdd(&g_rt_dbg[0], (unsigned long long)(tq1 - tq0)); atomicAdd(&g_rt_dbg[1], (unsigned long long)tq_wait); atomicAdd(&g_rt_dbg[2], (unsigned long long)tq_ld);
-        atomicAdd(&g_rt_dbg[3], (unsigned long long)tq_math); atomicAdd(&g_rt_dbg[4], (unsigned long long)(clock64() - tq2)); atomicAdd(&g_rt_dbg[5], 1ull);
-        atomicAdd(&g_rt_dbg[6], (unsigned long long)ntiles); atomicAdd(&g_rt_dbg2[3], (unsigned long long)tq_x[0]); atomicAdd(&g_rt_dbg2[4], (unsigned long long)tq_x[1]);
+        atomicAdd(&g_rt_dbg[0], (unsigned long long)(tq1 - tq0)); atomicAdd(&g_rt_dbg[1], (unsigned long long)(tq2 - tq1)); atomicAdd(&g_rt_dbg[4], (unsigned long long)(clock64() - tq2));
+        atomicAdd(&g_rt_dbg[5], 1ull); atomicAdd(&g_rt_dbg[6], (unsigned long long)ntiles);
     }
 #endif
     return r | (1 << 30);
@@ -790,8 +777,9 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
 
     if (tc_on) {
         if (threadIdx.x == 0) {
+            mbar_init(&sm.flush_go, 1);
+            for (int t = 0; t < 2 * RT_GROUPS; ++t) { mbar_init(&sm.acc_empty[t >> 1][t & 1], 4); mbar_init(&sm.acc_full[t >> 1][t & 1], 1); }
             for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], RT_GROUPS); }   // a stage is free once every group's MMAs have read it
-            for (int t = 0; t < 2 * RT_GROUPS; ++t) { mbar_init(&sm.acc_full[t >> 1][t & 1], 1); mbar_init(&sm.acc_empty[t >> 1][t & 1], 4); }
             mbar_fence_init();
             sm.tc_ntiles = 0;
         }
@@ -864,8 +852,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
     }
     if (tc_on) {                                                      // release the tensor-core warps
         rs_sync();
-        if (threadIdx.x == 0) sm.tc_ntiles = -1;
-        rs_sync_all();
+        if (threadIdx.x == 0) { sm.tc_ntiles = -1; mbar_arrive(&sm.flush_go); }
     }
 #ifdef RS_TIMING
     if (threadIdx.x == 0) {
@@ -1139,7 +1126,7 @@ namespace bfr {
 #ifdef RS_TIMING
 }
 extern "C" __attribute__((visibility("default"))) void bfr_dbg_ransac_counters(unsigned long long* out) { cudaMemcpyFromSymbol(out, bfr::g_rs_dbg, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(bfr::g_rs_dbg, z, 64); }
-extern "C" __attribute__((visibility("default"))) void bfr_dbg_ransac_tc_counters(unsigned long long* out) { cudaMemcpyFromSymbol(out, bfr::g_rt_dbg, 64); cudaMemcpyFromSymbol(out + 8, bfr::g_rt_dbg2, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(bfr::g_rt_dbg, z, 64); cudaMemcpyToSymbol(bfr::g_rt_dbg2, z, 64); }
+extern "C" __attribute__((visibility("default"))) void bfr_dbg_ransac_tc_counters(unsigned long long* out) { cudaMemcpyFromSymbol(out, bfr::g_rt_dbg, 64); unsigned long long z[8] = {0}; cudaMemcpyToSymbol(bfr::g_rt_dbg, z, 64); }
 namespace bfr {
 #endif
 // ---- host launchers -------------------------------------------------------------------------------------------

@@ -35,8 +35,6 @@ for s in splits:
         tot, sc, fit, n, nsc = [float(x) for x in o[:5]]
         print("  per CTA: total %.0f cycles = stage1 %.0f + fit %.0f + score %.0f; scored hypotheses/CTA %.1f" % (tot / n, (tot - fit) / n, (fit - sc) / n, sc / n, nsc / n))
         if hasattr(L, "bfr_dbg_ransac_tc_counters"):
-            o = np.zeros(16, dtype=np.uint64); L.bfr_dbg_ransac_tc_counters(ctypes.c_void_p(o.ctypes.data))
-            b, w, ld, m, r, nf, nt = [float(x) for x in o[:7]]
-            if o[10]: print("  issue path per issue: a_empty wait + TMA %.0f, a_full wait + MMA issue %.0f (%d issues); thread 0 per tile: tcgen05.ld %.0f, hand-back %.0f" % (float(o[8]) / float(o[10]), float(o[9]) / float(o[10]), int(o[10]), float(o[11]) / nt, float(o[12]) / nt))
-            if o[10]: print("  per issue: a_full wait %.0f, fence + 2 MMAs %.0f, 2 commits %.0f; thread 0 per tile: fence + syncwarp %.0f" % (float(o[13]) / float(o[10]), float(o[14]) / float(o[10]), float(o[15]) / float(o[10]), float(o[7]) / nt))
-            if nf: print("  tensor flush (thread 0): %.0f flushes/CTA, %.1f tiles/flush; cycles per flush: build %.0f, acc wait %.0f, tmem ld %.0f, math %.0f, reduce %.0f" % (nf / n, nt / nf, b / nf, w / nf, ld / nf, m / nf, r / nf))
+            o = np.zeros(8, dtype=np.uint64); L.bfr_dbg_ransac_tc_counters(ctypes.c_void_p(o.ctypes.data))
+            b, loop, r, nf, nt = float(o[0]), float(o[1]), float(o[4]), float(o[5]), float(o[6])
+            if nf: print("  tensor flush (thread 0): %.0f flushes/CTA, %.1f A tiles/flush; cycles per flush: B operands %.0f, tile loop %.0f (%.0f per tile), count reduction %.0f" % (nf / n, nt / nf, b / nf, loop / nf, loop / nt, r / nf))

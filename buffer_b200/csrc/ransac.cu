@@ -38,7 +38,7 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_LAUNCH = RS_THREADS + 128;     // + four warps that feed the tensor core, one per epilogue warp group (20 warps: 96 registers, like 17 would be)
 constexpr int RS_CHUNK = 5120;                  // correspondences per shared-memory chunk; pairs with K <= RS_CHUNK stay resident
 #ifndef RS_S1_N
-#define RS_S1_N 4
+#define RS_S1_N 8
 #endif
 constexpr int RS_S1 = RS_S1_N;                     // stage-1 hypotheses per thread and round
 constexpr int RS_QCAP = 2 * RS_THREADS;            // queue 2 (exact scoring): < RS_THREADS leftovers plus the survivors of one fit block
@@ -194,11 +194,31 @@ BFR_DEVINL void load_sample_smem(const RsSmem& sm, const uint32_t id[3], float s
     for (int i = 0; i < 3; ++i) load_record_smem(sm, id[i], s[i], q[i]);
 }
 
+// Stage 1 of one hypothesis.  RES (samples in shared memory): branch-free - the repeated-index test, all three gathers and all three edge
+// tests are always evaluated and combined at the end (same comparisons as edge_lengths_ok, so the same verdict), which lets the RS_S1
+// hypotheses of a thread interleave: with early exits they ran one after another, each waiting for its own Philox chain and gathers.
 template <bool RES>
 BFR_DEVINL bool precheck(const RsSmem& sm, const float4* __restrict__ corr_p, uint32_t K, uint64_t seed, uint32_t pair_id, uint32_t h, float sim2)
 {
     uint32_t id[3];
     sample3(seed, pair_id, h, K, id);
+#ifndef RS_S1_BRANCHY
+    if (RES) {
+        float s[3][3], q[3][3];
+        load_sample_smem(sm, id, s, q);
+        bool ok = (id[0] != id[1]) & (id[0] != id[2]) & (id[1] != id[2]);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int a = (e == 2) ? 1 : 0, b = (e == 0) ? 1 : 2;
+            float dx = __fsub_rn(s[a][0], s[b][0]), dy = __fsub_rn(s[a][1], s[b][1]), dz = __fsub_rn(s[a][2], s[b][2]);
+            const float ds2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
+            dx = __fsub_rn(q[a][0], q[b][0]); dy = __fsub_rn(q[a][1], q[b][1]); dz = __fsub_rn(q[a][2], q[b][2]);
+            const float dt2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, __fmul_rn(dz, dz)));
+            ok &= !((ds2 < __fmul_rn(dt2, sim2)) | (dt2 < __fmul_rn(ds2, sim2)));
+        }
+        return ok;
+    }
+#endif
     if (id[0] == id[1] || id[0] == id[2] || id[1] == id[2]) return false;
     float s[3][3], q[3][3];
     if (RES) load_sample_smem(sm, id, s, q); else load_sample(corr_p, id, s, q);
@@ -657,7 +677,8 @@ BFR_DEVINL void ransac_item(RsSmem& sm, const float4* __restrict__ corr_p, int K
 #pragma unroll
             for (int u = 0; u < RS_S1; ++u) {
                 hh[u] = base + (uint32_t)u * RS_THREADS + threadIdx.x;
-                ok[u] = hh[u] < he && precheck<RES>(sm, corr_p, (uint32_t)K, seed, pair_id, hh[u], sim2);
+                ok[u] = RES ? (precheck<RES>(sm, corr_p, (uint32_t)K, seed, pair_id, hh[u], sim2) & (hh[u] < he))        // (a hypothesis index past the range draws valid samples too)
+                            : (hh[u] < he && precheck<RES>(sm, corr_p, (uint32_t)K, seed, pair_id, hh[u], sim2));
             }
 #ifdef RS_TIMING
             tm[0] += clock64() - ts_;

@@ -54,14 +54,15 @@ constexpr int RT_N = RT_GROUPS * 64;            // B rows of a flush (a group's 
 constexpr int RT_QCAP = RT_FLUSH + RS_THREADS;  // queue 2 (tensor-core scoring): < RT_FLUSH leftovers plus the survivors of one fit block
 constexpr int RT_TILE = 128;                    // correspondences per A tile (MMA M)
 constexpr int RT_TILE_BYTES = RT_TILE * 32;     // K = 16 f16 per row
-constexpr int RT_STAGES = 8;                    // A tiles in flight (TMA ring): the MMAs run two tiles ahead of the epilogue, the copies five more
+constexpr int RT_STAGES = 8;                    // A tiles in shared memory: two super-stages of RT_SUPER tiles
+constexpr int RT_SUPER = 4;                     // A tiles per TMA copy and per full / empty barrier pair
 constexpr int RT_MAX_TILES = RS_CHUNK / RT_TILE;
 constexpr int RT_MIN_TC = 48;                    // smaller flushes (the tail of an item) are cheaper on the exact FP32 loop than 40 tile hand-offs
 constexpr float RT_RANGE = 8192.0f;             // largest |s|_1, |q_i|, |t_i| the f16 splits are used for (beyond: exact FP32 scoring)
 constexpr float RT_PAD_Q = 32768.0f;            // target coordinate of the padding rows of the last A tile: never an inlier, never in the band
 
 #ifdef RS_TRACE
-constexpr int RTR_EV = 8, RTR_TILES = 20;
+constexpr int RTR_EV = 8, RTR_TILES = 12;
 __device__ unsigned int g_trace[20 * RTR_EV * RTR_TILES];      // clocks of lane 0 of every warp of CTA 0 during one flush: [warp][tile][event]
 #define RTR(ev, tile) { if (trace_on && lane == 0 && (tile) < RTR_TILES) sm.trace[warp][(tile) * RTR_EV + (ev)] = (unsigned)clock64(); }
 #else
@@ -102,7 +103,7 @@ struct __align__(1024) RsSmem {
     int qcount;
     uint32_t tmem_base;
 #ifdef RS_TRACE
-    unsigned int trace[20][8 * 20];
+    unsigned int trace[20][8 * 12];
 #endif
     uint32_t stat[4];                           // float bits: max |s|_1, max |q_i| of the pair, max |t_i| of the flush; [3] != 0: out of range / non-finite
 };
@@ -349,11 +350,12 @@ BFR_DEVINL void rt_issue_tile(uint32_t tmem_d, uint32_t a_lo, uint32_t b1_lo, ui
                  "tcgen05.fence::after_thread_sync;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db1, %5, pf;\n\t"
                  "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db2, %5, pt;\n\t"
-                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t"
-                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%7];\n\t}"
-                 ::"r"(tmem_d), "r"(a_lo), "r"(b1_lo), "r"(b2_lo), "r"(RT_DESC_HI), "r"(idesc), "r"(bar_acc_full), "r"(bar_a_empty) : "memory");
+                 "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%6];\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b1_lo), "r"(b2_lo), "r"(RT_DESC_HI), "r"(idesc), "r"(bar_acc_full) : "memory");
+    if (bar_a_empty)                                                  // last tile of an A super-stage: it is free once these (and all earlier) MMAs have completed
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_a_empty) : "memory");
 }
-static_assert(RT_STAGES == 8, "the ring index is taken with a mask");
+static_assert(RT_STAGES == 2 * RT_SUPER, "two super-stages");
 BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scratch, int grp)
 {
     const int lane = threadIdx.x & 31;
@@ -362,42 +364,48 @@ BFR_DEVINL void tc_warp_loop(RsSmem& sm, const unsigned char* __restrict__ scrat
     const uint32_t b1_lo = rt_desc_lo(sm.u.tc.b_op[0]) + (uint32_t)(grp * (64 * 32 >> 4)), b2_lo = rt_desc_lo(sm.u.tc.b_op[1]) + (uint32_t)(grp * (64 * 32 >> 4));
     const uint32_t bar_af = smem_u32(&sm.a_full[0]), bar_ae = smem_u32(&sm.a_empty[0]), bar_cf = smem_u32(&sm.acc_full[grp][0]);
     const uint32_t ring = smem_u32(sm.u.tc.a_ring[0]);
-    uint32_t g0 = 0;                                                  // A tiles consumed before this flush
+    // The A tiles travel in super-tiles of RT_SUPER = 4 (one 16 KB TMA copy, one full / empty barrier pair per super-stage, two
+    // super-stages): per tile the issuing thread then waits for nothing but the hand-back of its accumulator buffer and commits once -
+    // every asynchronous operation on that path costs it ~100 cycles.
+    uint32_t g0 = 0, G0 = 0;                                          // A tiles / super-tiles consumed before this flush
     for (uint32_t flush = 0;; ++flush) {
         mbar_wait(&sm.flush_go, flush & 1u);
         const int ntiles = *reinterpret_cast<volatile int*>(&sm.tc_ntiles);
         if (ntiles < 0) break;
+        const int nst = (ntiles + RT_SUPER - 1) / RT_SUPER;
         if (lane == 0) {
-            // The A-tile copies are dealt out over the four warps (tile j by warp j % 4), RT_AHEAD tiles ahead of the issue: the copy of tile
-            // i + RT_AHEAD goes into the stage of tile i + RT_AHEAD - 8 and waits until every group's MMAs on that tile have completed, so the
-            // groups may drift 8 - RT_AHEAD tiles apart before a fast group's warp blocks (the slowest group's warp never does: no deadlock).
+            // super-tile j of this flush -> its super-stage, once every group's MMAs on the previous occupant have completed; the copies are
+            // dealt out over the four warps (super-tile G by warp G % 4)
             auto load = [&](int j) {
-                const uint32_t gj = g0 + (uint32_t)j, st = gj & (RT_STAGES - 1);
-                if (gj >= (uint32_t)RT_STAGES) mbar_wait(&sm.a_empty[st], ((gj / RT_STAGES) & 1u) ^ 1u);     // (the first occupant of a stage waits for nobody)
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_af + st * 8u), "r"((uint32_t)RT_TILE_BYTES) : "memory");
+                const uint32_t G = G0 + (uint32_t)j, ss = G & 1u;
+                if (G >= 2u) mbar_wait(&sm.a_empty[ss], ((G >> 1) & 1u) ^ 1u);
+                const uint32_t bytes = (uint32_t)min(RT_SUPER, ntiles - RT_SUPER * j) * RT_TILE_BYTES;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_af + ss * 8u), "r"(bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(ring + st * RT_TILE_BYTES), "l"(scratch + (size_t)j * RT_TILE_BYTES), "r"((uint32_t)RT_TILE_BYTES), "r"(bar_af + st * 8u) : "memory");
+                             ::"r"(ring + ss * (RT_SUPER * RT_TILE_BYTES)), "l"(scratch + (size_t)j * (RT_SUPER * RT_TILE_BYTES)), "r"(bytes), "r"(bar_af + ss * 8u) : "memory");
             };
-            constexpr int RT_AHEAD = 4;
-            if (grp < ntiles) load(grp);                              // tiles 0 .. 3
-            if (ntiles > 0) mbar_wait(&sm.a_full[g0 & (RT_STAGES - 1)], (g0 / RT_STAGES) & 1u);
+            if ((G0 & 3u) == (uint32_t)grp) load(0);
+            if (nst > 1 && ((G0 + 1u) & 3u) == (uint32_t)grp) load(1);
             for (int i = 0; i < ntiles; ++i) {
-                const uint32_t gi = g0 + (uint32_t)i, st = gi & (RT_STAGES - 1), buf = gi & 1u;
+                const int j = i / RT_SUPER, sub = i % RT_SUPER;
+                const uint32_t G = G0 + (uint32_t)j, ss = G & 1u, gi = g0 + (uint32_t)i, buf = gi & 1u;
 #ifdef RS_TRACE
                 const bool trace_on = blockIdx.x == 0 && g0 >= 80u && g0 < 120u; const int warp = threadIdx.x >> 5;
 #endif
                 RTR(0, i);
-                if (gi >= 2u) mbar_wait(&sm.acc_empty[grp][buf], ((gi >> 1) & 1u) ^ 1u);   // the group's four warps have pulled the buffer's previous tile out of TMEM
+                if (sub == 0) mbar_wait(&sm.a_full[ss], (G >> 1) & 1u);               // the super-tile has landed
                 RTR(1, i);
+                if (gi >= 2u) mbar_wait(&sm.acc_empty[grp][buf], ((gi >> 1) & 1u) ^ 1u);   // the group's four warps have pulled the buffer's previous tile out of TMEM
                 RTR(2, i);
-                rt_issue_tile(tmem_grp + buf * 64u, a_lo0 + st * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_cf + buf * 8u, bar_ae + st * 8u);
+                const bool last = sub == RT_SUPER - 1 || i == ntiles - 1;
+                rt_issue_tile(tmem_grp + buf * 64u, a_lo0 + (ss * RT_SUPER + (uint32_t)sub) * (RT_TILE_BYTES >> 4), b1_lo, b2_lo, bar_cf + buf * 8u, last ? bar_ae + ss * 8u : 0u);
                 RTR(3, i);
-                // behind the issue, while the group is busy with the other buffer: this warp's copy, and the A tile of the next issue
-                const int j = i + RT_AHEAD;
-                if (j < ntiles && (j & (RT_GROUPS - 1)) == grp) load(j);
-                if (i + 1 < ntiles) mbar_wait(&sm.a_full[(gi + 1u) & (RT_STAGES - 1)], ((gi + 1u) / RT_STAGES) & 1u);
+                // behind the second issue of super-tile j: the copy of super-tile j + 1 into the other super-stage (free once every group is
+                // done with super-tile j - 1, which by now they normally are; the slowest group's warp never waits here)
+                if (sub == 1 && j + 1 < nst && j + 1 >= 2 && ((G + 1u) & 3u) == (uint32_t)grp) load(j + 1);
             }
         }
+        G0 += (uint32_t)nst;
         g0 += (uint32_t)ntiles;
         __syncwarp();
     }
@@ -800,7 +808,7 @@ ransac_kernel(const float4* __restrict__ corr, const int32_t* __restrict__ corr_
         if (threadIdx.x == 0) {
             mbar_init(&sm.flush_go, 1);
             for (int t = 0; t < 2 * RT_GROUPS; ++t) { mbar_init(&sm.acc_empty[t >> 1][t & 1], 4); mbar_init(&sm.acc_full[t >> 1][t & 1], 1); }
-            for (int s = 0; s < RT_STAGES; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], RT_GROUPS); }   // a stage is free once every group's MMAs have read it
+            for (int s = 0; s < 2; ++s) { mbar_init(&sm.a_full[s], 1); mbar_init(&sm.a_empty[s], RT_GROUPS); }   // a super-stage is free once every group's MMAs have read it
             mbar_fence_init();
             sm.tc_ntiles = 0;
         }
@@ -1141,7 +1149,7 @@ lrf_vote_select_kernel(const float4* __restrict__ corr, const int32_t* __restric
 
 #ifdef RS_TRACE
 }
-extern "C" __attribute__((visibility("default"))) unsigned bfr_dbg_ransac_trace(unsigned* out) { cudaMemcpyFromSymbol(out, bfr::g_trace, sizeof(unsigned) * 20 * 8 * 20); return 20 * 8 * 20; }
+extern "C" __attribute__((visibility("default"))) unsigned bfr_dbg_ransac_trace(unsigned* out) { cudaMemcpyFromSymbol(out, bfr::g_trace, sizeof(unsigned) * 20 * 8 * 12); return 20 * 8 * 12; }
 namespace bfr {
 #endif
 #ifdef RS_TIMING

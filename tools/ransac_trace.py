@@ -9,7 +9,7 @@ import numpy as np, torch
 from buffer_b200 import _lib
 _lib.SO_PATH = os.path.abspath(os.environ.get("BFR_SO", "variants/lib_tr.so"))
 from buffer_b200 import backend as B, synthetic as S
-NT = 20
+NT = 12
 c = S.CONFIGS[2]; N = c["gen"]["num_kpts"]; dev = "cuda:0"; P = 148
 b = S.make_pairs(P, first_pair=0, device=dev, **c["gen"])
 off = (torch.arange(P + 1, dtype=torch.int32) * N).to(dev)
@@ -22,13 +22,13 @@ t0 = ev[:, 0, 0].min()
 rel = lambda x: int((x - t0) & 0xffffffff)
 for w in (0, 1, 4, 7, 8, 9, 15):
     line = []
-    for i in range(8, 14):
+    for i in range(4, 10):
         e = ev[w, i]
         line.append("%d: W%d F%d L%d H%d M%d" % (i, rel(e[0]), rel(e[1]), rel(e[2]), rel(e[4]), rel(e[5])))
     print("warp %2d | " % w + " | ".join(line))
 for g in range(4):
-    print("issuer %d | " % g + " | ".join("%d: wait-empty %d, seen %d, A tile %d, issued %d" % (i, rel(iss[g, i, 0]), rel(iss[g, i, 1]), rel(iss[g, i, 2]), rel(iss[g, i, 3])) for i in range(8, 12)))
-print("issuer means: buffer wait %.0f, A-tile wait %.0f, issue %.0f; hand-back of the group's last warp -> issued %.0f; issued -> first warp sees the tile %.0f" % (
+    print("issuer %d | " % g + " | ".join("%d: start %d, A tile there %d, buffer back %d, issued %d" % (i, rel(iss[g, i, 0]), rel(iss[g, i, 1]), rel(iss[g, i, 2]), rel(iss[g, i, 3])) for i in range(4, 8)))
+print("issuer means: A-tile wait %.0f, buffer wait %.0f, issue %.0f; hand-back of the group's last warp -> issued %.0f; issued -> first warp sees the tile %.0f" % (
     float(np.mean((iss[:, 2:, 1] - iss[:, 2:, 0]) & 0xffffffff)), float(np.mean((iss[:, 2:, 2] - iss[:, 2:, 1]) & 0xffffffff)), float(np.mean((iss[:, 2:, 3] - iss[:, 2:, 2]) & 0xffffffff)),
     float(np.mean([((iss[g, 4:, 3] - ev[4 * g:4 * g + 4, 2:-2, 4].max(0)) & 0xffffffff).mean() for g in range(4)])),
     float(np.mean([((ev[4 * g:4 * g + 4, 4:, 1].min(0) - iss[g, 4:, 3]) & 0xffffffff).mean() for g in range(4)]))))

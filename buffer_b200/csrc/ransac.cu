@@ -88,7 +88,7 @@ struct __align__(1024) RsSmem {
             unsigned char b_op[2][RT_N * 32];                 // [B1 | B2]: 256 (hypothesis, component) rows x 16 f16, group g = rows 64 g ..
             float q[12][RT_QCAP];
             uint32_t qh[RT_QCAP];
-            int cnt[RT_FLUSH];                                // inlier counts of the hypotheses of the current flush
+            int wcnt[RS_WARPS][RT_HT];                        // per-warp inlier counts of the group's hypotheses (current flush)
         } tc;
     } u;
     uint32_t q1[RS_Q1CAP];                      // queue 1: survivors of the cheap checks (hypothesis index); idle: partial counts / round results
@@ -458,7 +458,6 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     const long long tq0 = clock64();
 #endif
     // ---- B operands of the flush + the largest |t_i| ----
-    if (threadIdx.x < RT_FLUSH) sm.u.tc.cnt[threadIdx.x] = 0;
     float tm = 0.0f; bool bad = false;
     if ((int)threadIdx.x < 3 * n) {
         const int hl = (int)threadIdx.x / 3, comp = (int)threadIdx.x - 3 * hl, qi = base + hl;
@@ -580,7 +579,7 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
 #pragma unroll
         for (int j = 0; j < RT_HT; ++j) {
             const int tot = __reduce_add_sync(0xffffffffu, j < 10 ? c0[j % 10] : c1[j % 10]);
-            if (lane == j) atomicAdd(&sm.u.tc.cnt[hl0 + j], tot);
+            if (lane == j) sm.u.tc.wcnt[warp][j] = tot;
         }
     }
 #ifdef RS_TIMING
@@ -591,7 +590,11 @@ __device__ __noinline__ int tc_flush(int K, int base, int n, float d2max, float 
     if (trace_on) for (int k = threadIdx.x; k < 20 * RTR_EV * RTR_TILES; k += RS_THREADS) g_trace[k] = (&sm.trace[0][0])[k];
     else if (blockIdx.x == 0 && tile0 < 40u) for (int k = threadIdx.x; k < 20 * RTR_EV * RTR_TILES; k += RS_THREADS) (&sm.trace[0][0])[k] = 0u;
 #endif
-    const int r = (int)threadIdx.x < n ? sm.u.tc.cnt[threadIdx.x] : 0;
+    int r = 0;                                                        // hypothesis t of the flush: group t / 20, sum over the group's four warps
+    if ((int)threadIdx.x < n) {
+        const int g4 = 4 * ((int)threadIdx.x / RT_HT), j = (int)threadIdx.x % RT_HT;
+        r = sm.u.tc.wcnt[g4][j] + sm.u.tc.wcnt[g4 + 1][j] + sm.u.tc.wcnt[g4 + 2][j] + sm.u.tc.wcnt[g4 + 3][j];
+    }
     if (threadIdx.x == 0) { sm.stat[2] = 0u; sm.stat[3] = 0u; }
     rs_sync();
 #ifdef RS_TIMING

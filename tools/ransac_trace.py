@@ -27,10 +27,9 @@ for w in (0, 1, 4, 7, 8, 9, 15):
         line.append("%d: W%d F%d L%d H%d M%d" % (i, rel(e[0]), rel(e[1]), rel(e[2]), rel(e[4]), rel(e[5])))
     print("warp %2d | " % w + " | ".join(line))
 for g in range(4):
-    print("issuer %d | " % g + " | ".join("%d: start %d, A tile there %d, buffer back %d, issued %d" % (i, rel(iss[g, i, 0]), rel(iss[g, i, 1]), rel(iss[g, i, 2]), rel(iss[g, i, 3])) for i in range(4, 8)))
-print("issuer means: A-tile wait %.0f, buffer wait %.0f, issue %.0f; hand-back of the group's last warp -> issued %.0f; issued -> first warp sees the tile %.0f" % (
-    float(np.mean((iss[:, 2:, 1] - iss[:, 2:, 0]) & 0xffffffff)), float(np.mean((iss[:, 2:, 2] - iss[:, 2:, 1]) & 0xffffffff)), float(np.mean((iss[:, 2:, 3] - iss[:, 2:, 2]) & 0xffffffff)),
-    float(np.mean([((iss[g, 4:, 3] - ev[4 * g:4 * g + 4, 2:-2, 4].max(0)) & 0xffffffff).mean() for g in range(4)])),
-    float(np.mean([((ev[4 * g:4 * g + 4, 4:, 1].min(0) - iss[g, 4:, 3]) & 0xffffffff).mean() for g in range(4)]))))
+    print("issuer %d | " % g + " | ".join("%d: start %d, A tile there %d, buffer back %d, issued %d" % (i, rel(iss[g, i, 0]), rel(iss[g, i, 1]), rel(iss[g, i, 2]), rel(iss[g, i, 3])) for i in range(2, NT) if iss[g, i, 3]))
 d = lambda a, b: float(np.mean((ev[:, 2:, a] - ev[:, 2:, b]) & 0xffffffff))
 print("means over warps and tiles: wait %.0f, ld %.0f, hand back %.0f, math %.0f, tile period %.0f" % (d(1, 0), d(2, 1), d(4, 2), d(5, 4), float(np.mean((ev[:, 3:, 0] - ev[:, 2:-1, 0]) & 0xffffffff))))
+if os.environ.get("BFR_TRACE_ALL"):
+    for w in range(16):
+        print("warp %2d | " % w + " | ".join("%d: W%d F%d L%d H%d M%d" % (i, rel(ev[w, i, 0]), rel(ev[w, i, 1]), rel(ev[w, i, 2]), rel(ev[w, i, 4]), rel(ev[w, i, 5])) for i in range(2, NT)))
